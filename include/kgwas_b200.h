@@ -1,0 +1,146 @@
+/*
+ * kgwas_b200.h -- C ABI of libkgwas_b200.so, the sm_100a message-passing engine behind
+ * kgwas_b200's drop-in HeteroGNN / HeteroConv / SAGEConv / GATConv.
+ *
+ * The reference (snap-stanford/KGWAS) has no FFI of its own: its hot path is Python calling
+ * torch_geometric.  Each entry point below cites the reference interface whose arithmetic it
+ * replaces (paths relative to /root/reference).  Conventions:
+ *   - every pointer is a DEVICE pointer owned by the caller (torch), unless named h_*;
+ *   - every call takes the CUDA stream to launch on and never synchronises the device,
+ *     never allocates: scratch is a caller-supplied workspace sized by *_workspace_bytes();
+ *   - return value 0 = ok, negative = KGB_ERR_*; kgb_last_error() gives the thread-local text;
+ *   - node features are row-major fp32 with an explicit row stride (in floats); feature widths
+ *     must be a multiple of 32 and <= 512; indices are int32 on the device side
+ *     (int64 COO at the graph boundary, as PyG's edge_index is).
+ */
+#ifndef KGWAS_B200_H_
+#define KGWAS_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define KGB_API __attribute__((visibility("default")))
+#else
+#define KGB_API
+#endif
+
+typedef void* kgb_stream_t; /* cudaStream_t */
+
+enum {
+  KGB_OK = 0,
+  KGB_ERR_INVALID = -1,   /* bad argument (shape, alignment, null pointer) */
+  KGB_ERR_WORKSPACE = -2, /* workspace too small */
+  KGB_ERR_CUDA = -3,      /* a CUDA runtime call failed; see kgb_last_error() */
+  KGB_ERR_UNSUPPORTED = -4
+};
+
+/* ---- library identity ------------------------------------------------------------- */
+KGB_API int kgb_version(void);            /* MAJOR*10000 + MINOR*100 + PATCH */
+KGB_API int kgb_sm_arch(void);            /* 100 : compiled for sm_100a only */
+KGB_API const char* kgb_last_error(void); /* thread-local, never NULL */
+
+/* ---- graph bookkeeping ------------------------------------------------------------ */
+/* COO (PyG edge_index [2,E] int64, unsorted, duplicates allowed; kgwas/model.py:53
+ * `edge_index_dict`) -> CSR by destination + CSR by source ("transposed"), both with STABLE
+ * edge order (ties keep original edge order) so results are bit-reproducible:
+ *   rowptr  [n_dst+1]  col  [E] = src of the e-th edge in dst-major order
+ *   eperm   [E]        original edge id of CSR slot i      (carries GAT alpha back to COO order)
+ *   t_rowptr[n_src+1]  t_col[E] = dst of the j-th edge in src-major order
+ *   t_eperm [E]        CSR slot of transposed slot j       (weights_csc = weights_csr[t_eperm])
+ * Replaces the index handling inside PyG MessagePassing.propagate / scatter (reached from
+ * kgwas/conv.py:182 and kgwas/model.py:74).  Any of the t_* outputs may be NULL (all three). */
+KGB_API size_t kgb_csr_build_workspace_bytes(int64_t n_edges, int64_t n_src, int64_t n_dst);
+KGB_API int kgb_csr_build(const int64_t* src, const int64_t* dst, int64_t n_edges, int64_t n_src,
+                  int64_t n_dst, int32_t* rowptr, int32_t* col, int32_t* eperm,
+                  int32_t* t_rowptr, int32_t* t_col, int32_t* t_eperm, void* workspace,
+                  size_t workspace_bytes, kgb_stream_t stream);
+
+/* Rows longer than seg_len are split into fixed-length segments that are reduced by separate
+ * warps and combined in segment order (deterministic).  Two-phase: count, then fill.
+ *   hrow_id    [n_hrows]    row index of each heavy row (ascending)
+ *   hrow_segptr[n_hrows+1]  prefix sum of segments per heavy row
+ *   hseg_hrow  [n_hsegs]    heavy-row slot of each segment
+ * h_counts (HOST, 2 ints) receives {n_hrows, n_hsegs}; this one call synchronises the stream. */
+KGB_API int kgb_csr_heavy_count(const int32_t* rowptr, int32_t n_rows, int32_t seg_len, int32_t* h_counts,
+                        void* workspace, size_t workspace_bytes, kgb_stream_t stream);
+KGB_API size_t kgb_csr_heavy_workspace_bytes(int32_t n_rows);
+KGB_API int kgb_csr_heavy_fill(const int32_t* rowptr, int32_t n_rows, int32_t seg_len, int32_t n_hrows,
+                       int32_t n_hsegs, int32_t* hrow_id, int32_t* hrow_segptr, int32_t* hseg_hrow,
+                       void* workspace, size_t workspace_bytes, kgb_stream_t stream);
+
+/* ---- segmented gather-reduce (the message-passing core) --------------------------- */
+/* y[i,:] = act( beta*y[i,:] + sum_{j in [rowptr[i], rowptr[i+1])} w_j * x[col[j], :] )
+ *   w_j = ew ? ew[wperm ? wperm[j] : j] : 1          rowsum2[i] = sum_j ew2[wperm ? wperm[j] : j]
+ * One pass: gather -> weighted segmented reduce -> write; no [E,h] message tensor, no atomics
+ * on the data path.  Replaces index_select + scatter_add(/mean) of SAGEConv (PyG; instantiated
+ * kgwas/model.py:38; mean = precomputed 1/deg edge weights) and `alpha.unsqueeze(-1) * x_j` +
+ * 'add' aggregation of GATConv (kgwas/conv.py:227-228, :54); run on the transposed CSR (with
+ * wperm = t_eperm so the weights stay in CSR order) it is their backward (index_add / gather).
+ * heavy_* come from kgb_csr_heavy_*; pass n_hrows = n_hsegs = 0 when no row exceeds seg_len.
+ * scratch: kgb_spmm_scratch_bytes(), zero-initialised ONCE by the caller (the kernel leaves its
+ * ticket counters zero again on exit); may be NULL when n_hsegs == 0. */
+typedef struct {
+  const int32_t* rowptr;
+  const int32_t* col;
+  int32_t n_rows;
+  int32_t seg_len;
+  int32_t n_hrows;
+  int32_t n_hsegs;
+  const int32_t* hrow_id;
+  const int32_t* hrow_segptr;
+  const int32_t* hseg_hrow;
+} kgb_csr_t;
+
+KGB_API size_t kgb_spmm_scratch_bytes(int32_t n_hrows, int32_t n_hsegs, int32_t h);
+KGB_API int kgb_spmm(const kgb_csr_t* csr, const float* ew, const int32_t* wperm, const float* ew2,
+                     float* rowsum2, const float* x, int64_t ldx, float* y, int64_t ldy, int32_t h,
+                     float beta, int32_t relu, void* scratch, size_t scratch_bytes,
+                     kgb_stream_t stream);
+
+/* ---- dense contractions ([nodes x in] . [in x out]) ------------------------------- */
+/* C[M,N] = act( alpha * op(A).op(B) + beta*C + bias[N] )      (row-major, strides in floats)
+ *   layout KGB_NT : A[M,K] (lda), B[N,K] (ldb)   C = A.B^T     forward  x.W^T   (PyG Linear,
+ *                                                              kgwas/model.py:38,50; conv.py:81-89)
+ *   layout KGB_NN : A[M,K] (lda), B[K,N] (ldb)   C = A.B       dX = G.W
+ *   layout KGB_TN : A[K,M] (lda), B[K,N] (ldb)   C = A^T.B     dW = G^T.X  (K = node rows)
+ * fp32 in / fp32 out; accumulation is fp32-equivalent (3xTF32 split on the tensor cores for the
+ * tcgen05 path, FFMA for small or odd shapes).  Needs N % 4 == 0, and K % 4 == 0 (NT/NN) or
+ * M % 4 == 0 (TN).  workspace: kgb_gemm_workspace_bytes() (split-K partials). */
+enum { KGB_NT = 0, KGB_NN = 1, KGB_TN = 2 };
+KGB_API size_t kgb_gemm_workspace_bytes(int32_t layout, int64_t m, int64_t n, int64_t k);
+KGB_API int kgb_gemm(int32_t layout, const float* a, int64_t lda, const float* b, int64_t ldb,
+                     float* c, int64_t ldc, int64_t m, int64_t n, int64_t k, float alpha,
+                     float beta, const float* bias, int32_t relu, void* workspace,
+                     size_t workspace_bytes, kgb_stream_t stream);
+
+/* ---- small fused elementwise / reduction helpers ---------------------------------- */
+/* g[i] = dy[i] * (y[i] > 0)          backward of `x.relu()` (kgwas/model.py:75)          */
+KGB_API int kgb_relu_bwd(const float* dy, const float* y, float* g, int64_t n, kgb_stream_t stream);
+/* out[s, :] = beta*out[s, :] + sum_m w[m, s] * x[m, :]   (w NULL -> plain column sum, n_slots 1)
+ * db_l of SAGEConv.lin_l / GATConv.bias, and d(att-folded vectors) of GATConv. */
+KGB_API size_t kgb_wcolsum_workspace_bytes(int64_t m, int32_t n_slots, int32_t h);
+KGB_API int kgb_wcolsum(const float* x, int64_t ldx, const float* w, int64_t ldw, int64_t m,
+                        int32_t n_slots, int32_t h, float* out, float beta, void* workspace,
+                        size_t workspace_bytes, kgb_stream_t stream);
+/* a[i, s] = <x[i, s*slot_stride : s*slot_stride + h], v[s, :]>   node-level attention logits
+ * alpha_src / alpha_dst (kgwas/conv.py:150-151) for n_slots relations at once
+ * (slot_stride 0: every slot reads the same row). */
+KGB_API int kgb_rowdot(const float* x, int64_t ldx, int64_t n_rows, int32_t n_slots, int32_t h,
+                       int64_t slot_stride, const float* v, float* a, int64_t lda,
+                       kgb_stream_t stream);
+/* y[i, :] = beta*y[i, :] + sum_s a[i, s] * v[s, :]   (backward of kgb_rowdot w.r.t. x) */
+KGB_API int kgb_rank_update(const float* a, int64_t lda, int32_t n_slots, const float* v, float* y,
+                            int64_t ldy, int64_t n_rows, int32_t h, float beta, kgb_stream_t stream);
+/* out[j] = w[perm[j]]  (edge weights CSR order -> COO order / transposed order) */
+KGB_API int kgb_permute_f32(const float* w, const int32_t* perm, float* out, int64_t n,
+                            kgb_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KGWAS_B200_H_ */

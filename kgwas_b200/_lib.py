@@ -1,0 +1,294 @@
+"""ctypes binding of libkgwas_b200.so (C ABI declared in include/kgwas_b200.h).
+
+There is no CPU fallback: if the shared library is missing, or a tensor is not a CUDA tensor,
+the call raises.  Build the library in-tree with ``python kgwas_b200/csrc/build.py``
+(``__graft_entry__.build()`` does it).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libkgwas_b200.so")
+
+KGB_NT, KGB_NN, KGB_TN = 0, 1, 2
+
+_lib = None
+launches = 0          # number of kernel-launching C-ABI calls made (bench.py reports it)
+
+
+class KgbError(RuntimeError):
+    pass
+
+
+class CsrStruct(C.Structure):
+    _fields_ = [("rowptr", C.c_void_p), ("col", C.c_void_p), ("n_rows", C.c_int32), ("seg_len", C.c_int32),
+                ("n_hrows", C.c_int32), ("n_hsegs", C.c_int32), ("hrow_id", C.c_void_p),
+                ("hrow_segptr", C.c_void_p), ("hseg_hrow", C.c_void_p)]
+
+
+_P, _I32, _I64, _F, _SZ = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_size_t
+
+# name -> (restype, argtypes); must list EVERY symbol include/kgwas_b200.h declares
+SIGNATURES = {
+    "kgb_version": (C.c_int, []),
+    "kgb_sm_arch": (C.c_int, []),
+    "kgb_last_error": (C.c_char_p, []),
+    "kgb_csr_build_workspace_bytes": (_SZ, [_I64, _I64, _I64]),
+    "kgb_csr_build": (C.c_int, [_P, _P, _I64, _I64, _I64, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
+    "kgb_csr_heavy_count": (C.c_int, [_P, _I32, _I32, _P, _P, _SZ, _P]),
+    "kgb_csr_heavy_workspace_bytes": (_SZ, [_I32]),
+    "kgb_csr_heavy_fill": (C.c_int, [_P, _I32, _I32, _I32, _I32, _P, _P, _P, _P, _SZ, _P]),
+    "kgb_spmm_scratch_bytes": (_SZ, [_I32, _I32, _I32]),
+    "kgb_spmm": (C.c_int, [C.POINTER(CsrStruct), _P, _P, _P, _P, _P, _I64, _P, _I64, _I32, _F, _I32, _P, _SZ, _P]),
+    "kgb_gemm_workspace_bytes": (_SZ, [_I32, _I64, _I64, _I64]),
+    "kgb_gemm": (C.c_int, [_I32, _P, _I64, _P, _I64, _P, _I64, _I64, _I64, _I64, _F, _F, _P, _I32, _P, _SZ, _P]),
+    "kgb_relu_bwd": (C.c_int, [_P, _P, _P, _I64, _P]),
+    "kgb_wcolsum_workspace_bytes": (_SZ, [_I64, _I32, _I32]),
+    "kgb_wcolsum": (C.c_int, [_P, _I64, _P, _I64, _I64, _I32, _I32, _P, _F, _P, _SZ, _P]),
+    "kgb_rowdot": (C.c_int, [_P, _I64, _I64, _I32, _I32, _I64, _P, _P, _I64, _P]),
+    "kgb_rank_update": (C.c_int, [_P, _I64, _I32, _P, _P, _I64, _I64, _I32, _F, _P]),
+    "kgb_permute_f32": (C.c_int, [_P, _P, _P, _I64, _P]),
+}
+
+
+def get_lib():
+    """Load the shared library (once).  Raises if it has not been built: no fallback."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise KgbError(f"{LIB_PATH} not found: the CUDA extension is required (no CPU / PyTorch fallback). "
+                           "Build it with `python kgwas_b200/csrc/build.py`.")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = lib
+    return _lib
+
+
+def _check(rc: int, what: str):
+    if rc != 0:
+        raise KgbError(f"{what} failed (rc={rc}): {get_lib().kgb_last_error().decode()}")
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise KgbError("kgwas_b200 kernels need CUDA tensors (there is no CPU path); got a CPU tensor")
+
+
+def _f32c(t, name):
+    if t.dtype != torch.float32 or t.stride(-1) != 1:
+        raise KgbError(f"{name}: expected fp32 with unit inner stride, got {t.dtype} {tuple(t.stride())}")
+
+
+# ---------------------------------------------------------------------------------------------
+# graph bookkeeping
+# ---------------------------------------------------------------------------------------------
+
+SEG_LEN = 256
+
+
+class Csr:
+    """CSR of a bipartite edge set + optional transposed CSR + heavy-row segmentation."""
+
+    def __init__(self, rowptr, col, n_rows, n_cols, seg_len=SEG_LEN):
+        self.rowptr, self.col, self.n_rows, self.n_cols, self.seg_len = rowptr, col, n_rows, n_cols, seg_len
+        self.n_hrows = self.n_hsegs = 0
+        self.hrow_id = self.hrow_segptr = self.hseg_hrow = None
+        self._scratch = {}
+        self._build_heavy()
+        self.struct = CsrStruct(_ptr(rowptr), _ptr(col), n_rows, seg_len, self.n_hrows, self.n_hsegs,
+                                _ptr(self.hrow_id), _ptr(self.hrow_segptr), _ptr(self.hseg_hrow))
+
+    @property
+    def n_edges(self):
+        return self.col.numel()
+
+    def _build_heavy(self):
+        if self.n_rows == 0 or self.col.numel() <= self.seg_len:
+            return
+        lib = get_lib()
+        dev = self.rowptr.device
+        ws_bytes = lib.kgb_csr_heavy_workspace_bytes(self.n_rows)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        counts = (C.c_int32 * 2)()
+        _check(lib.kgb_csr_heavy_count(_ptr(self.rowptr), self.n_rows, self.seg_len, counts, _ptr(ws), ws_bytes,
+                                       _stream()), "kgb_csr_heavy_count")
+        self.n_hrows, self.n_hsegs = int(counts[0]), int(counts[1])
+        if self.n_hrows == 0:
+            return
+        self.hrow_id = torch.empty(self.n_hrows, dtype=torch.int32, device=dev)
+        self.hrow_segptr = torch.empty(self.n_hrows + 1, dtype=torch.int32, device=dev)
+        self.hseg_hrow = torch.empty(self.n_hsegs, dtype=torch.int32, device=dev)
+        _check(lib.kgb_csr_heavy_fill(_ptr(self.rowptr), self.n_rows, self.seg_len, self.n_hrows, self.n_hsegs,
+                                      _ptr(self.hrow_id), _ptr(self.hrow_segptr), _ptr(self.hseg_hrow), _ptr(ws),
+                                      ws_bytes, _stream()), "kgb_csr_heavy_fill")
+
+    def scratch(self, h: int):
+        """Per-CSR scratch for heavy-row partials (zeroed once; kernels leave the tickets zero)."""
+        if self.n_hsegs == 0:
+            return None, 0
+        if h not in self._scratch:
+            nbytes = get_lib().kgb_spmm_scratch_bytes(self.n_hrows, self.n_hsegs, h)
+            self._scratch[h] = torch.zeros(nbytes, dtype=torch.uint8, device=self.rowptr.device)
+        s = self._scratch[h]
+        return s, s.numel()
+
+
+def csr_build(src: torch.Tensor, dst: torch.Tensor, n_src: int, n_dst: int, transposed: bool = True,
+              seg_len: int = SEG_LEN):
+    """COO (int64) -> (Csr by dst, eperm, Csr by src | None, t_eperm | None) via kgb_csr_build."""
+    _need_cuda(src, dst)
+    if src.dtype != torch.int64 or dst.dtype != torch.int64:
+        raise KgbError("csr_build: edge indices must be int64")
+    src, dst = src.contiguous(), dst.contiguous()
+    E, dev = src.numel(), src.device
+    lib = get_lib()
+    i32 = dict(dtype=torch.int32, device=dev)
+    rowptr, col, eperm = torch.empty(n_dst + 1, **i32), torch.empty(E, **i32), torch.empty(E, **i32)
+    t_rowptr = t_col = t_eperm = None
+    if transposed:
+        t_rowptr, t_col, t_eperm = torch.empty(n_src + 1, **i32), torch.empty(E, **i32), torch.empty(E, **i32)
+    ws_bytes = lib.kgb_csr_build_workspace_bytes(E, n_src, n_dst)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    global launches
+    launches += 1
+    _check(lib.kgb_csr_build(_ptr(src), _ptr(dst), E, n_src, n_dst, _ptr(rowptr), _ptr(col), _ptr(eperm),
+                             _ptr(t_rowptr), _ptr(t_col), _ptr(t_eperm), _ptr(ws), ws_bytes, _stream()),
+           "kgb_csr_build")
+    fwd = Csr(rowptr, col, n_dst, n_src, seg_len)
+    bwd = Csr(t_rowptr, t_col, n_src, n_dst, seg_len) if transposed else None
+    return fwd, eperm, bwd, t_eperm
+
+
+# ---------------------------------------------------------------------------------------------
+# compute
+# ---------------------------------------------------------------------------------------------
+
+
+def spmm(csr: Csr, x: torch.Tensor, y: torch.Tensor, h: int, *, ew=None, wperm=None, ew2=None, rowsum2=None,
+         beta: float = 0.0, relu: bool = False):
+    """y[i,:h] = act(beta*y[i,:h] + sum_j w_j x[col_j,:h]).  x / y are 2-D views with row strides."""
+    _need_cuda(x, y, ew, wperm, ew2, rowsum2)
+    _f32c(x, "spmm x"); _f32c(y, "spmm y")
+    if csr.n_rows == 0:
+        return y
+    if csr.n_edges == 0:
+        if beta == 0.0:
+            y[:, :h].zero_()
+        elif relu:
+            y[:, :h].clamp_(min=0)
+        if rowsum2 is not None:
+            rowsum2.zero_()
+        return y
+    scratch, nbytes = csr.scratch(h)
+    global launches
+    launches += 1
+    _check(get_lib().kgb_spmm(C.byref(csr.struct), _ptr(ew), _ptr(wperm), _ptr(ew2), _ptr(rowsum2), _ptr(x),
+                              x.stride(0), _ptr(y), y.stride(0), h, beta, int(relu), _ptr(scratch), nbytes,
+                              _stream()), "kgb_spmm")
+    return y
+
+
+_gemm_ws = {}
+
+
+def _workspace(nbytes: int, dev) -> Optional[torch.Tensor]:
+    if nbytes == 0:
+        return None
+    key = (dev.index, torch.cuda.current_stream().cuda_stream)
+    ws = _gemm_ws.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(nbytes, 1 << 22), dtype=torch.uint8, device=dev)
+        _gemm_ws[key] = ws
+    return ws
+
+
+def gemm(layout: int, a: torch.Tensor, b: torch.Tensor, c: torch.Tensor, m: int, n: int, k: int, *,
+         alpha: float = 1.0, beta: float = 0.0, bias=None, relu: bool = False):
+    """c[m,n] = act(alpha * op(a) op(b) + beta*c + bias); 2-D fp32 views, row strides honoured."""
+    _need_cuda(a, b, c, bias)
+    _f32c(a, "gemm a"); _f32c(b, "gemm b"); _f32c(c, "gemm c")
+    if m == 0 or n == 0:
+        return c
+    lib = get_lib()
+    ws_bytes = lib.kgb_gemm_workspace_bytes(layout, m, n, k)
+    ws = _workspace(ws_bytes, a.device)
+    global launches
+    launches += 1
+    _check(lib.kgb_gemm(layout, _ptr(a), a.stride(0), _ptr(b), b.stride(0), _ptr(c), c.stride(0), m, n, k,
+                        alpha, beta, _ptr(bias), int(relu), _ptr(ws), ws.numel() if ws is not None else 0,
+                        _stream()), "kgb_gemm")
+    return c
+
+
+def relu_bwd(dy: torch.Tensor, y: torch.Tensor, out: Optional[torch.Tensor] = None):
+    _need_cuda(dy, y)
+    dy, y = dy.contiguous(), y.contiguous()
+    if out is None:
+        out = torch.empty_like(dy)
+    global launches
+    launches += 1
+    _check(get_lib().kgb_relu_bwd(_ptr(dy), _ptr(y), _ptr(out), dy.numel(), _stream()), "kgb_relu_bwd")
+    return out
+
+
+def wcolsum(x: torch.Tensor, h: int, out: torch.Tensor, *, w=None, n_slots: int = 1, beta: float = 0.0):
+    """out[s,:h] = beta*out + sum_m w[m,s] x[m,:h]  (w None: plain column sum)."""
+    _need_cuda(x, out, w)
+    _f32c(x, "wcolsum x")
+    m = x.size(0)
+    if m == 0:
+        if beta == 0.0:
+            out.zero_()
+        return out
+    lib = get_lib()
+    nbytes = lib.kgb_wcolsum_workspace_bytes(m, n_slots, h)
+    ws = _workspace(nbytes, x.device)
+    global launches
+    launches += 1
+    _check(lib.kgb_wcolsum(_ptr(x), x.stride(0), _ptr(w), w.stride(0) if w is not None else 0, m, n_slots, h,
+                           _ptr(out), beta, _ptr(ws), ws.numel(), _stream()), "kgb_wcolsum")
+    return out
+
+
+def rowdot(x: torch.Tensor, v: torch.Tensor, a: torch.Tensor, h: int, n_slots: int, slot_stride: int):
+    _need_cuda(x, v, a)
+    global launches
+    launches += 1
+    _check(get_lib().kgb_rowdot(_ptr(x), x.stride(0), x.size(0), n_slots, h, slot_stride, _ptr(v), _ptr(a),
+                                a.stride(0), _stream()), "kgb_rowdot")
+    return a
+
+
+def rank_update(a: torch.Tensor, v: torch.Tensor, y: torch.Tensor, h: int, n_slots: int, beta: float):
+    _need_cuda(a, v, y)
+    global launches
+    launches += 1
+    _check(get_lib().kgb_rank_update(_ptr(a), a.stride(0), n_slots, _ptr(v), _ptr(y), y.stride(0), y.size(0), h,
+                                     beta, _stream()), "kgb_rank_update")
+    return y
+
+
+def permute_f32(w: torch.Tensor, perm: torch.Tensor, out: Optional[torch.Tensor] = None):
+    _need_cuda(w, perm)
+    if out is None:
+        out = torch.empty(perm.numel(), dtype=torch.float32, device=w.device)
+    global launches
+    launches += 1
+    _check(get_lib().kgb_permute_f32(_ptr(w), _ptr(perm), _ptr(out), perm.numel(), _stream()), "kgb_permute_f32")
+    return out

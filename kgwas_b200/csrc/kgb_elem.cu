@@ -1,0 +1,207 @@
+// Small fused elementwise / reduction helpers around the aggregation kernels.
+#include "kgb_common.cuh"
+
+namespace kgb {
+
+// g = dy * (y > 0)
+__global__ void k_relu_bwd(const float* __restrict__ dy, const float* __restrict__ y, float* __restrict__ g, int64_t n) {
+  const int64_t n4 = n >> 2;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 a = ldg_stream_f4(dy + 4 * i), b = ldg_stream_f4(y + 4 * i);
+    st_f4(g + 4 * i, make_float4(b.x > 0.f ? a.x : 0.f, b.y > 0.f ? a.y : 0.f, b.z > 0.f ? a.z : 0.f, b.w > 0.f ? a.w : 0.f));
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    const int64_t i = (n4 << 2) + threadIdx.x;
+    g[i] = y[i] > 0.f ? dy[i] : 0.f;
+  }
+}
+
+// Weighted column sums, stage 1:  part[b][r][:] = sum_{m in chunk b} w[m, r] * x[m, :]   (w == NULL -> 1, R = 1)
+constexpr int kColsumThreads = 256;
+template <int H, int R>
+__global__ void __launch_bounds__(kColsumThreads)
+k_wcolsum_stage1(const float* __restrict__ x, int64_t ldx, const float* __restrict__ w, int64_t ldw, int64_t M,
+                 int64_t rows_per_cta, float* __restrict__ part) {
+  __shared__ float red[kColsumThreads / 32][H];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta;
+  const int64_t r1 = min(M, r0 + rows_per_cta);
+  RowVec<H> acc[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) acc[r].zero();
+  for (int64_t m = r0 + warp; m < r1; m += kColsumThreads / 32) {
+    RowVec<H> t;
+    t.load(x + m * ldx, lane);
+    if (w) {
+#pragma unroll
+      for (int r = 0; r < R; ++r) acc[r].fma(__ldg(w + m * ldw + r), t);
+    } else {
+      acc[0].add(t);
+    }
+  }
+  // fold the 8 warps in warp order (fixed => deterministic)
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    __syncthreads();
+    acc[r].store(&red[warp][0], lane);
+    __syncthreads();
+    for (int c = threadIdx.x; c < H; c += kColsumThreads) {
+      float s = 0.f;
+#pragma unroll
+      for (int q = 0; q < kColsumThreads / 32; ++q) s += red[q][c];
+      part[((int64_t)blockIdx.x * R + r) * H + c] = s;
+    }
+  }
+}
+// stage 2: out[r][c] = beta*out + sum_b part[b][r][c]   (chunk order)
+__global__ void k_wcolsum_stage2(const float* __restrict__ part, int n_ctas, int RH, float* __restrict__ out, float beta) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= RH) return;
+  float s = 0.f;
+  for (int b = 0; b < n_ctas; ++b) s += part[(int64_t)b * RH + i];
+  out[i] = (beta != 0.f ? beta * out[i] : 0.f) + s;
+}
+
+// a[i, s] = <x[i, s*slot_stride : +h], v[s, :]>
+template <int H>
+__global__ void k_rowdot(const float* __restrict__ x, int64_t ldx, int64_t n_rows, int n_slots, int64_t slot_stride,
+                         const float* __restrict__ v, float* __restrict__ a, int64_t lda) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t row = warp0; row < n_rows; row += n_warps) {
+    RowVec<H> xr;
+    if (slot_stride == 0) xr.load(x + row * ldx, lane);
+    for (int s = 0; s < n_slots; ++s) {
+      if (slot_stride != 0) xr.load(x + row * ldx + s * slot_stride, lane);
+      RowVec<H> vs;
+      vs.load(v + (int64_t)s * H, lane);
+      const float d = warp_sum(xr.dot(vs));
+      if (lane == 0) a[row * lda + s] = d;
+    }
+  }
+}
+
+// y[i, :] = beta*y[i, :] + sum_s a[i, s] * v[s, :]      (rank-n_slots update; n_slots small)
+template <int H>
+__global__ void k_rank_update(const float* __restrict__ a, int64_t lda, int n_slots, const float* __restrict__ v,
+                              float* __restrict__ y, int64_t ldy, int64_t n_rows, float beta) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t row = warp0; row < n_rows; row += n_warps) {
+    RowVec<H> acc;
+    acc.zero();
+    for (int s = 0; s < n_slots; ++s) {
+      RowVec<H> vs;
+      vs.load(v + (int64_t)s * H, lane);
+      acc.fma(__ldg(a + row * lda + s), vs);
+    }
+    if (beta != 0.f) {
+      RowVec<H> old;
+      old.load_plain(y + row * ldy, lane);
+#pragma unroll
+      for (int i = 0; i < RowVec<H>::N; ++i) acc.v[i] = fmaf(beta, old.v[i], acc.v[i]);
+    }
+    acc.store(y + row * ldy, lane);
+  }
+}
+
+__global__ void k_permute_f32(const float* __restrict__ w, const int32_t* __restrict__ perm, float* __restrict__ out, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = __ldg(w + perm[i]);
+}
+
+inline unsigned warp_grid(int64_t n_warp_items, int threads) {
+  int64_t ctas = (n_warp_items + threads / 32 - 1) / (threads / 32);
+  const int64_t cap = (int64_t)kNumSMs * 32;
+  if (ctas > cap) ctas = cap;
+  return (unsigned)(ctas < 1 ? 1 : ctas);
+}
+
+static int64_t colsum_ctas(int64_t m) {
+  int64_t c = (m + 63) / 64;
+  if (c > 4 * kNumSMs) c = 4 * kNumSMs;
+  return c < 1 ? 1 : c;
+}
+
+}  // namespace kgb
+
+using namespace kgb;
+
+extern "C" int kgb_relu_bwd(const float* dy, const float* y, float* g, int64_t n, kgb_stream_t stream_) {
+  if (n == 0) return KGB_OK;
+  KGB_REQUIRE(dy && y && g && n > 0, "relu_bwd: bad argument");
+  KGB_REQUIRE(aligned16(dy) && aligned16(y) && aligned16(g), "relu_bwd: pointers must be 16-byte aligned");
+  int64_t ctas = (n / 4 + 255) / 256;
+  if (ctas > kNumSMs * 16) ctas = kNumSMs * 16;
+  if (ctas < 1) ctas = 1;
+  k_relu_bwd<<<(unsigned)ctas, 256, 0, (cudaStream_t)stream_>>>(dy, y, g, n);
+  KGB_LAUNCH_OK();
+  return KGB_OK;
+}
+
+extern "C" size_t kgb_wcolsum_workspace_bytes(int64_t m, int32_t n_slots, int32_t h) {
+  return (size_t)colsum_ctas(m) * (size_t)(n_slots > 0 ? n_slots : 1) * h * sizeof(float) + 256;
+}
+
+extern "C" int kgb_wcolsum(const float* x, int64_t ldx, const float* w, int64_t ldw, int64_t m, int32_t n_slots,
+                           int32_t h, float* out, float beta, void* workspace, size_t workspace_bytes,
+                           kgb_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  KGB_REQUIRE(x && out && m >= 0 && n_slots >= 1, "wcolsum: bad argument");
+  KGB_REQUIRE(w != nullptr || n_slots == 1, "wcolsum: n_slots > 1 needs weights");
+  KGB_REQUIRE(n_slots <= 8, "wcolsum: at most 8 slots per call");
+  KGB_REQUIRE(aligned16(x) && ldx % 4 == 0, "wcolsum: x alignment");
+  if (workspace_bytes < kgb_wcolsum_workspace_bytes(m, n_slots, h) || !workspace) {
+    set_error("wcolsum: workspace too small");
+    return KGB_ERR_WORKSPACE;
+  }
+  const int64_t ctas = colsum_ctas(m);
+  const int64_t rows_per_cta = (m + ctas - 1) / ctas;
+  float* part = static_cast<float*>(workspace);
+#define KGB_WCS(RR) k_wcolsum_stage1<H, RR><<<(unsigned)ctas, kColsumThreads, 0, stream>>>(x, ldx, w, ldw, m, rows_per_cta, part)
+  KGB_DISPATCH_H(h, {
+    switch (n_slots) {
+      case 1: KGB_WCS(1); break; case 2: KGB_WCS(2); break; case 3: KGB_WCS(3); break; case 4: KGB_WCS(4); break;
+      case 5: KGB_WCS(5); break; case 6: KGB_WCS(6); break; case 7: KGB_WCS(7); break; default: KGB_WCS(8); break;
+    }
+  });
+#undef KGB_WCS
+  KGB_LAUNCH_OK();
+  const int RH = n_slots * h;
+  k_wcolsum_stage2<<<(RH + 255) / 256, 256, 0, stream>>>(part, (int)ctas, RH, out, beta);
+  KGB_LAUNCH_OK();
+  return KGB_OK;
+}
+
+extern "C" int kgb_rowdot(const float* x, int64_t ldx, int64_t n_rows, int32_t n_slots, int32_t h, int64_t slot_stride,
+                          const float* v, float* a, int64_t lda, kgb_stream_t stream_) {
+  if (n_rows == 0) return KGB_OK;
+  KGB_REQUIRE(x && v && a && n_slots >= 1 && lda >= n_slots, "rowdot: bad argument");
+  KGB_REQUIRE(aligned16(x) && aligned16(v) && ldx % 4 == 0 && slot_stride % 4 == 0, "rowdot: alignment");
+  KGB_DISPATCH_H(h, (k_rowdot<H><<<warp_grid(n_rows, 256), 256, 0, (cudaStream_t)stream_>>>(x, ldx, n_rows, n_slots,
+                                                                                         slot_stride, v, a, lda)));
+  KGB_LAUNCH_OK();
+  return KGB_OK;
+}
+
+extern "C" int kgb_rank_update(const float* a, int64_t lda, int32_t n_slots, const float* v, float* y, int64_t ldy,
+                               int64_t n_rows, int32_t h, float beta, kgb_stream_t stream_) {
+  if (n_rows == 0) return KGB_OK;
+  KGB_REQUIRE(a && v && y && n_slots >= 1, "rank_update: bad argument");
+  KGB_REQUIRE(aligned16(v) && aligned16(y) && ldy % 4 == 0, "rank_update: alignment");
+  KGB_DISPATCH_H(h, (k_rank_update<H><<<warp_grid(n_rows, 256), 256, 0, (cudaStream_t)stream_>>>(a, lda, n_slots, v, y,
+                                                                                              ldy, n_rows, beta)));
+  KGB_LAUNCH_OK();
+  return KGB_OK;
+}
+
+extern "C" int kgb_permute_f32(const float* w, const int32_t* perm, float* out, int64_t n, kgb_stream_t stream_) {
+  if (n == 0) return KGB_OK;
+  KGB_REQUIRE(w && perm && out, "permute_f32: null pointer");
+  k_permute_f32<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream_>>>(w, perm, out, n);
+  KGB_LAUNCH_OK();
+  return KGB_OK;
+}

@@ -1,0 +1,196 @@
+// Segmented gather-reduce: y[i,:] = beta*y[i,:] + sum_j ew[j] * x[col[j],:]  over a CSR.
+//
+// HBM-bound byte work: one warp owns one destination row (or one fixed-length
+// segment of a heavy row); every gathered source row is one fully coalesced 128-bit-per-lane
+// request (512 B at h=128), index/weight slices are read 32 at a time and broadcast by shuffle,
+// four gathers are kept in flight per warp.  No [E,h] message tensor, no atomics on data.
+// Heavy rows (hub genes: in-degree 1e4..1e5) are cut into seg_len-edge segments; the last warp
+// to finish a row (ticket counter) folds the partials in segment order => deterministic.
+#include "kgb_common.cuh"
+
+namespace kgb {
+
+constexpr int kSpmmThreads = 256;  // 8 warps / CTA
+constexpr int kUnroll = 4;
+
+struct EdgeW {            // per-edge scalars riding along the gather
+  const float* ew;        // weight of the gathered row (NULL -> 1)
+  const int32_t* wperm;   // weights are indexed ew[wperm[slot]] when non-NULL (transposed CSR)
+  const float* ew2;       // second scalar, only row-summed (NULL -> unused)
+};
+
+template <int H>
+__device__ __forceinline__ void gather_accumulate(RowVec<H>& acc, float& sum2, const int32_t* __restrict__ col,
+                                                  const EdgeW& e, const float* __restrict__ x,
+                                                  int64_t ldx, int start, int end, int lane) {
+  for (int base = start; base < end; base += kWarp) {
+    const int n = min(kWarp, end - base);
+    int c = 0;
+    float w = 0.f;
+    if (lane < n) {
+      c = __ldg(col + base + lane);
+      const int wi = e.wperm ? __ldg(e.wperm + base + lane) : base + lane;
+      w = e.ew ? __ldg(e.ew + wi) : 1.f;
+      if (e.ew2) sum2 += __ldg(e.ew2 + wi);
+    }
+    int j = 0;
+    for (; j + kUnroll <= n; j += kUnroll) {
+      RowVec<H> t[kUnroll];
+      float wj[kUnroll];
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        const int cj = __shfl_sync(0xffffffffu, c, j + u);
+        wj[u] = __shfl_sync(0xffffffffu, w, j + u);
+        t[u].load(x + (int64_t)cj * ldx, lane);
+      }
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) acc.fma(wj[u], t[u]);
+    }
+    for (; j < n; ++j) {
+      const int cj = __shfl_sync(0xffffffffu, c, j);
+      const float wj = __shfl_sync(0xffffffffu, w, j);
+      RowVec<H> t;
+      t.load(x + (int64_t)cj * ldx, lane);
+      acc.fma(wj, t);
+    }
+  }
+}
+
+template <int H>
+__device__ __forceinline__ void write_row(const RowVec<H>& acc, float* __restrict__ yrow, float beta, int relu,
+                                          int lane) {
+  RowVec<H> out = acc;
+  if (beta != 0.f) {
+    RowVec<H> old;
+    old.load_plain(yrow, lane);
+#pragma unroll
+    for (int i = 0; i < RowVec<H>::N; ++i) out.v[i] = fmaf(beta, old.v[i], out.v[i]);
+  }
+  if (relu) {
+#pragma unroll
+    for (int i = 0; i < RowVec<H>::N; ++i) out.v[i] = fmaxf(out.v[i], 0.f);
+  }
+  out.store(yrow, lane);
+}
+
+// Work items: [0, n_hsegs) heavy segments (long tasks first), then one item per row.
+template <int H>
+__global__ void __launch_bounds__(kSpmmThreads)
+k_spmm(kgb_csr_t g, EdgeW e, const float* __restrict__ x, int64_t ldx, float* __restrict__ y, int64_t ldy, float beta,
+       int relu, float* __restrict__ rowsum2, float* __restrict__ partial, float* __restrict__ partial2,
+       int32_t* __restrict__ ticket) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int64_t n_items = (int64_t)g.n_hsegs + g.n_rows;
+  for (int64_t item = warp0; item < n_items; item += n_warps) {
+    if (item < g.n_hsegs) {
+      const int seg = (int)item;
+      const int hr = __ldg(g.hseg_hrow + seg);
+      const int row = __ldg(g.hrow_id + hr);
+      const int seg0 = __ldg(g.hrow_segptr + hr), seg1 = __ldg(g.hrow_segptr + hr + 1);
+      const int rs = __ldg(g.rowptr + row), re = __ldg(g.rowptr + row + 1);
+      const int start = rs + (seg - seg0) * g.seg_len;
+      const int end = min(re, start + g.seg_len);
+      RowVec<H> acc;
+      acc.zero();
+      float s2 = 0.f;
+      gather_accumulate<H>(acc, s2, g.col, e, x, ldx, start, end, lane);
+      acc.store(partial + (int64_t)seg * H, lane);
+      if (rowsum2) {
+        s2 = warp_sum(s2);
+        if (lane == 0) partial2[seg] = s2;
+      }
+      __threadfence();  // publish this partial before taking a ticket
+      int t = 0;
+      if (lane == 0) t = atomicAdd(ticket + hr, 1);
+      t = __shfl_sync(0xffffffffu, t, 0);
+      if (t == seg1 - seg0 - 1) {  // last segment of the row to finish: fold in segment order
+        __threadfence();
+        RowVec<H> sum;
+        sum.zero();
+        for (int s = seg0; s < seg1; ++s) {
+          RowVec<H> p;
+          p.load_plain(partial + (int64_t)s * H, lane);
+          sum.add(p);
+        }
+        write_row<H>(sum, y + (int64_t)row * ldy, beta, relu, lane);
+        if (rowsum2 && lane == 0) {
+          float t2 = 0.f;
+          for (int s = seg0; s < seg1; ++s) t2 += __ldcg(partial2 + s);
+          rowsum2[row] = t2;
+        }
+        if (lane == 0) ticket[hr] = 0;  // leave the counters clean for the next launch
+      }
+    } else {
+      const int row = (int)(item - g.n_hsegs);
+      const int start = __ldg(g.rowptr + row), end = __ldg(g.rowptr + row + 1);
+      if (end - start > g.seg_len && g.n_hsegs > 0) continue;  // heavy: handled above
+      RowVec<H> acc;
+      acc.zero();
+      float s2 = 0.f;
+      gather_accumulate<H>(acc, s2, g.col, e, x, ldx, start, end, lane);
+      write_row<H>(acc, y + (int64_t)row * ldy, beta, relu, lane);
+      if (rowsum2) {
+        s2 = warp_sum(s2);
+        if (lane == 0) rowsum2[row] = s2;
+      }
+    }
+  }
+}
+
+inline unsigned spmm_grid(int64_t n_items) {
+  const int64_t warps_per_cta = kSpmmThreads / 32;
+  int64_t ctas = (n_items + warps_per_cta - 1) / warps_per_cta;
+  const int64_t cap = (int64_t)kNumSMs * 8 * 4;  // 8 resident CTAs/SM x 4 waves, grid-stride beyond
+  if (ctas > cap) ctas = cap;
+  if (ctas < 1) ctas = 1;
+  return (unsigned)ctas;
+}
+
+int check_csr(const kgb_csr_t* g, const char* who) {
+  KGB_REQUIRE(g && g->rowptr && g->n_rows >= 0, "%s: bad csr", who);
+  KGB_REQUIRE(g->seg_len > 0, "%s: seg_len must be > 0", who);
+  KGB_REQUIRE(g->n_hsegs == 0 || (g->hrow_id && g->hrow_segptr && g->hseg_hrow), "%s: heavy arrays missing", who);
+  return KGB_OK;
+}
+
+}  // namespace kgb
+
+using namespace kgb;
+
+extern "C" size_t kgb_spmm_scratch_bytes(int32_t n_hrows, int32_t n_hsegs, int32_t h) {
+  return align_up((size_t)n_hsegs * h * sizeof(float), 256) + align_up((size_t)n_hsegs * sizeof(float), 256) +
+         align_up((size_t)n_hrows * sizeof(int32_t), 256) + 256;
+}
+
+extern "C" int kgb_spmm(const kgb_csr_t* csr, const float* ew, const int32_t* wperm, const float* ew2, float* rowsum2,
+                        const float* x, int64_t ldx, float* y, int64_t ldy, int32_t h, float beta, int32_t relu,
+                        void* scratch, size_t scratch_bytes, kgb_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (int rc = check_csr(csr, "spmm")) return rc;
+  if (csr->n_rows == 0) return KGB_OK;
+  KGB_REQUIRE(x && y, "spmm: null x/y");
+  KGB_REQUIRE(ldx >= h && ldy >= h && ldx % 4 == 0 && ldy % 4 == 0, "spmm: strides must be >= h and multiples of 4");
+  KGB_REQUIRE(aligned16(x) && aligned16(y), "spmm: x/y must be 16-byte aligned");
+  KGB_REQUIRE((ew2 == nullptr) == (rowsum2 == nullptr), "spmm: ew2 and rowsum2 go together");
+  float* partial = nullptr;
+  float* partial2 = nullptr;
+  int32_t* ticket = nullptr;
+  if (csr->n_hsegs > 0) {
+    if (scratch_bytes < kgb_spmm_scratch_bytes(csr->n_hrows, csr->n_hsegs, h) || !scratch) {
+      set_error("spmm: scratch %zu < %zu", scratch_bytes, kgb_spmm_scratch_bytes(csr->n_hrows, csr->n_hsegs, h));
+      return KGB_ERR_WORKSPACE;
+    }
+    Carver ws(scratch);
+    ticket = ws.take<int32_t>(csr->n_hrows);  // counters first: caller zeroes them once
+    partial2 = ws.take<float>((size_t)csr->n_hsegs);
+    partial = ws.take<float>((size_t)csr->n_hsegs * h);
+  }
+  const EdgeW e{ew, wperm, ew2};
+  const unsigned grid = spmm_grid((int64_t)csr->n_hsegs + csr->n_rows);
+  KGB_DISPATCH_H(h, (k_spmm<H><<<grid, kSpmmThreads, 0, stream>>>(*csr, e, x, ldx, y, ldy, beta, relu, rowsum2, partial, partial2,
+                                                               ticket)));
+  KGB_LAUNCH_OK();
+  return KGB_OK;
+}

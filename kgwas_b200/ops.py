@@ -1,0 +1,166 @@
+"""Autograd boundary of the engine: one ``torch.autograd.Function`` per heterogeneous layer.
+
+Forward and backward call only the C-ABI kernels of libkgwas_b200 (via ``_lib``); PyTorch is used
+for allocation, tiny parameter reshuffles ([h,h]-sized stack / permute / sum) and autograd
+plumbing.  Semantics follow PyG ``HeteroConv`` + ``SAGEConv`` as used by kgwas/model.py:34-48,74
+(SURVEY.md Appendix A.1-A.2); the per-relation Python loop of the reference becomes one merged
+gather-reduce per (destination type, source type) pair -- see plan.py.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import torch
+
+from . import _lib
+from ._lib import KGB_NN, KGB_NT, KGB_TN
+from .plan import LayerPlan
+
+
+def _empty(rows, cols, like):
+    return torch.empty((rows, cols), dtype=torch.float32, device=like.device)
+
+
+class _SageLayerCtx:
+    """Static description handed to the autograd Function (not a tensor)."""
+
+    def __init__(self, plan: LayerPlan, node_types: List[str], h: int, relu: bool, rel_scale: Dict[str, float]):
+        self.plan, self.node_types, self.h, self.relu, self.rel_scale = plan, node_types, h, relu, rel_scale
+
+
+class HeteroSageLayerFn(torch.autograd.Function):
+    """out[T] = act( scale_T * sum_{r into T} [ lin_l^r(mean_{e in r} x_src) + lin_r^r(x_T) ] )
+
+    inputs : one [N,h] tensor per node type in ``meta.node_types``, then per relation (in
+             ``plan.rel_order`` order) lin_l.weight [h,h] x R, lin_l.bias [h] x R, lin_r.weight [h,h] x R.
+    outputs: one [N_T,h] tensor per destination type in ``plan.dst_types`` order.
+    Relations whose destination type receives no gradient get ``None`` (not zeros), exactly like
+    autograd in the reference (those parameters are then skipped by Adam, kgwas/kgwas.py:116,151).
+    """
+
+    @staticmethod
+    def forward(ctx, meta: _SageLayerCtx, *tensors):
+        plan, h = meta.plan, meta.h
+        nt, nr = len(meta.node_types), len(plan.rel_order)
+        xs = tensors[:nt]
+        Wl = torch.stack(tensors[nt:nt + nr])
+        bl = torch.stack(tensors[nt + nr:nt + 2 * nr])
+        Wr = torch.stack(tensors[nt + 2 * nr:nt + 3 * nr])
+        ctx.set_materialize_grads(False)
+        x = dict(zip(meta.node_types, [t.contiguous() for t in xs]))
+        outs, saved_A = [], {}
+        for T in plan.dst_types:
+            a, b = plan.rel_range[T]
+            scale = meta.rel_scale[T]
+            n_t = plan.num_nodes[T]
+            out = _empty(n_t, h, Wl)
+            first = True
+            for job in plan.jobs[T]:
+                lo, hi = job.rel_ids[0], job.rel_ids[-1] + 1
+                R, xs_ = job.R, x[job.src_type]
+                if job.mode == "xf":
+                    wcat = Wl[lo:hi].reshape(R * h, h)                       # view: rows k*h.. = W_l^k
+                    z = _empty(job.n_src, R * h, Wl)
+                    _lib.gemm(KGB_NT, xs_, wcat, z, job.n_src, R * h, h, alpha=scale)
+                    _lib.spmm(job.csr, z.view(job.n_src * R, h), out, h, ew=job.w_mean, beta=0.0 if first else 1.0)
+                else:
+                    A = _empty(n_t, R * h, Wl)
+                    _lib.spmm(job.csr, xs_, A.view(n_t * R, h), h, ew=job.w_mean)
+                    wcat_t = Wl[lo:hi].permute(1, 0, 2).reshape(h, R * h)    # [h, R*h]: out += A . wcat_t^T
+                    _lib.gemm(KGB_NT, A, wcat_t, out, n_t, h, R * h, alpha=scale, beta=0.0 if first else 1.0)
+                    saved_A[(T, job.src_type)] = A
+                first = False
+            w_root = Wr[a:b].sum(0)
+            bias = bl[a:b].sum(0)
+            if scale != 1.0:
+                bias = bias * scale
+            _lib.gemm(KGB_NT, x[T], w_root, out, n_t, h, h, alpha=scale, beta=0.0 if first else 1.0, bias=bias,
+                      relu=meta.relu)
+            outs.append(out)
+        ctx.meta = meta
+        ctx.saved_A = saved_A
+        ctx.save_for_backward(Wl, Wr, *[x[t] for t in meta.node_types], *outs)
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *d_outs):
+        meta: _SageLayerCtx = ctx.meta
+        plan, h = meta.plan, meta.h
+        saved = ctx.saved_tensors
+        Wl, Wr = saved[0], saved[1]
+        n_types, nr = len(meta.node_types), len(plan.rel_order)
+        x = dict(zip(meta.node_types, saved[2:2 + n_types]))
+        outs = dict(zip(plan.dst_types, saved[2 + n_types:]))
+        need_x = dict(zip(meta.node_types, ctx.needs_input_grad[1:1 + n_types]))
+        need_p = ctx.needs_input_grad[1 + n_types:]
+        need_w = any(need_p)
+
+        dWl = torch.zeros_like(Wl) if need_w else None
+        dbl = torch.zeros((Wl.size(0), h), dtype=torch.float32, device=Wl.device) if need_w else None
+        dWr = torch.zeros_like(Wr) if need_w else None
+        used = [False] * nr                                      # relations that received a gradient
+        dx: Dict[str, Optional[torch.Tensor]] = {t: None for t in meta.node_types}
+
+        def dx_target(t):
+            """(buffer, beta) for accumulating into d x[t]."""
+            if dx[t] is None:
+                dx[t] = _empty(plan.num_nodes[t], h, Wl)
+                return dx[t], 0.0
+            return dx[t], 1.0
+
+        for T, d_out in zip(plan.dst_types, d_outs):
+            if d_out is None:
+                continue
+            a, b = plan.rel_range[T]
+            scale = meta.rel_scale[T]
+            n_t = plan.num_nodes[T]
+            g = _lib.relu_bwd(d_out, outs[T]) if meta.relu else d_out.contiguous()
+            if scale != 1.0:
+                g = g * scale
+            for i in range(a, b):
+                used[i] = True
+            if need_w:
+                db = torch.empty(h, dtype=torch.float32, device=g.device)
+                _lib.wcolsum(g, h, db)
+                dbl[a:b] = db
+                dwr = _empty(h, h, g)
+                _lib.gemm(KGB_TN, g, x[T], dwr, h, h, n_t)
+                dWr[a:b] = dwr
+            if need_x[T]:
+                buf, beta = dx_target(T)
+                _lib.gemm(KGB_NN, g, Wr[a:b].sum(0), buf, n_t, h, h, beta=beta)
+            for job in plan.jobs[T]:
+                lo, hi = job.rel_ids[0], job.rel_ids[-1] + 1
+                R, S = job.R, job.src_type
+                if job.mode == "xf":
+                    dz = _empty(job.n_src, R * h, g)
+                    _lib.spmm(job.tcsr, g, dz.view(job.n_src * R, h), h, ew=job.w_mean, wperm=job.t_eperm)
+                    if need_w:
+                        _lib.gemm(KGB_TN, dz, x[S], dWl[lo:hi].view(R * h, h), R * h, h, job.n_src)
+                    if need_x[S]:
+                        buf, beta = dx_target(S)
+                        _lib.gemm(KGB_NN, dz, Wl[lo:hi].reshape(R * h, h), buf, job.n_src, h, R * h, beta=beta)
+                else:
+                    A = ctx.saved_A[(T, S)]
+                    if need_w:
+                        dwt = _empty(h, R * h, g)                              # [h_out, R*h_in]
+                        _lib.gemm(KGB_TN, g, A, dwt, h, R * h, n_t)
+                        dWl[lo:hi] = dwt.view(h, R, h).permute(1, 0, 2)
+                    if need_x[S]:
+                        wcat_t = Wl[lo:hi].permute(1, 0, 2).reshape(h, R * h)
+                        dA = _empty(n_t, R * h, g)
+                        _lib.gemm(KGB_NN, g, wcat_t, dA, n_t, R * h, h)
+                        buf, beta = dx_target(S)
+                        _lib.spmm(job.tcsr, dA.view(n_t * R, h), buf, h, ew=job.w_mean, wperm=job.t_eperm, beta=beta)
+        ctx.saved_A = None
+        grads_x = []
+        for t in meta.node_types:
+            if need_x[t] and dx[t] is None:      # no gradient reached this type: autograd treats None as zero
+                grads_x.append(None)
+            else:
+                grads_x.append(dx[t] if need_x[t] else None)
+        grads_p = []
+        for k, stacked in enumerate((dWl, dbl, dWr)):
+            for i in range(nr):
+                grads_p.append(stacked[i] if (used[i] and need_p[k * nr + i]) else None)
+        return (None, *grads_x, *grads_p)

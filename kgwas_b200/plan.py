@@ -1,0 +1,143 @@
+"""Execution plan of one heterogeneous convolution over a fixed ``edge_index_dict``.
+
+The reference loops over relations in Python and materialises one ``[N_dst, h]`` tensor per
+relation before stacking and summing them (PyG ``HeteroConv`` + ``group``; in-tree echo
+kgwas/conv.py:17-32).  Here all relations between one (destination type, source type) pair are
+merged into ONE bipartite job with a single CSR (+ transposed CSR for the backward pass):
+
+* ``xf`` ("transform first", chosen when N_src <= N_dst, e.g. Gene -> SNP): the per-relation linear
+  map is applied on the small source side, ``Z = X_src . [W_1; ..; W_R]^T`` (``[N_src, R*h]`` viewed
+  as ``[N_src*R, h]``), and the job gathers row ``s*R + k`` of Z straight into the destination row;
+* ``af`` ("aggregate first", N_src > N_dst, e.g. SNP -> Gene): the job reduces into virtual rows
+  ``t*R + k`` (``A = [N_dst, R*h]``) and the linear map ``A . [W_1 | .. | W_R]^T`` runs on the small
+  destination side.
+
+Both are legal because mean / sum / attention-weighted aggregation commute with the linear map.
+Edges of a job are sorted by (t, k) with ties in original edge order, so a softmax group
+(relation k, destination t) is a contiguous slot range in either mode.
+"""
+from __future__ import annotations
+
+from collections import OrderedDict
+from typing import Dict, List, Tuple
+
+import torch
+
+from . import _lib
+
+EdgeType = Tuple[str, str, str]
+
+
+class PairJob:
+    def __init__(self, dst_type: str, src_type: str, rels: List[EdgeType], rel_ids: List[int],
+                 edge_indices: List[torch.Tensor], n_src: int, n_dst: int):
+        self.dst_type, self.src_type, self.rels, self.rel_ids = dst_type, src_type, rels, rel_ids
+        self.R, self.n_src, self.n_dst = len(rels), n_src, n_dst
+        self.mode = "xf" if n_src <= n_dst else "af"
+        R = self.R
+        dev = edge_indices[0].device
+        sizes = [int(ei.size(1)) for ei in edge_indices]
+        self.edge_offsets = [0]
+        for s in sizes:
+            self.edge_offsets.append(self.edge_offsets[-1] + s)
+        self.n_edges = self.edge_offsets[-1]
+        src = torch.cat([ei[0] for ei in edge_indices])
+        dst = torch.cat([ei[1] for ei in edge_indices])
+        slot = torch.cat([torch.full((s,), k, dtype=torch.int64, device=dev) for k, s in enumerate(sizes)])
+        group = dst * R + slot                                   # softmax / mean group of every edge
+        if self.mode == "xf":
+            job_src, job_dst, n_js, n_jd = src * R + slot, dst, n_src * R, n_dst
+        else:
+            job_src, job_dst, n_js, n_jd = src, group, n_src, n_dst * R
+        self.csr, self.eperm, self.tcsr, self.t_eperm = _lib.csr_build(job_src, job_dst, n_js, n_jd)
+        # group bookkeeping (exact integer work; plan time only)
+        deg = torch.bincount(group, minlength=n_dst * R)
+        self.group_deg = deg.to(torch.int32)
+        w = (1.0 / deg.clamp(min=1).to(torch.float32))[group]    # SAGE mean: 1 / max(in-degree, 1)
+        self.w_mean = w[self.eperm.long()].contiguous()          # CSR slot order
+        if self.mode == "xf":
+            # slots are (t, k)-sorted; group row pointers over the same slot order
+            gp = torch.zeros(n_dst * R + 1, dtype=torch.int64, device=dev)
+            torch.cumsum(deg, 0, out=gp[1:])
+            self.group_rowptr = gp.to(torch.int32)
+        else:
+            self.group_rowptr = self.csr.rowptr
+        self.group_of_slot = group[self.eperm.long()].to(torch.int32).contiguous()
+
+    def __repr__(self):
+        return (f"PairJob({self.src_type}->{self.dst_type}, R={self.R}, mode={self.mode}, E={self.n_edges}, "
+                f"heavy_rows={self.csr.n_hrows}/{self.tcsr.n_hrows})")
+
+
+class LayerPlan:
+    """All jobs of one ``edge_index_dict``; shared by every layer of the model."""
+
+    def __init__(self, edge_index_dict: Dict[EdgeType, torch.Tensor], num_nodes: Dict[str, int],
+                 conv_keys=None):
+        self.edge_types: List[EdgeType] = [et for et in edge_index_dict
+                                           if (conv_keys is None or et in conv_keys)
+                                           and et[0] in num_nodes and et[2] in num_nodes]
+        self.num_nodes = dict(num_nodes)
+        # relation order: grouped by (dst type, src type) in first-appearance order, so that a job's
+        # relations are contiguous in the stacked parameter tensors
+        pair_order: "OrderedDict[Tuple[str, str], List[EdgeType]]" = OrderedDict()
+        dst_order: List[str] = []
+        for et in self.edge_types:
+            if et[2] not in dst_order:
+                dst_order.append(et[2])
+        for T in dst_order:
+            for et in self.edge_types:
+                if et[2] == T:
+                    pair_order.setdefault((T, et[0]), []).append(et)
+        self.dst_types = dst_order
+        self.rel_order: List[EdgeType] = [et for rels in pair_order.values() for et in rels]
+        self.rel_index = {et: i for i, et in enumerate(self.rel_order)}
+        self.jobs: Dict[str, List[PairJob]] = {T: [] for T in dst_order}
+        self.rel_range: Dict[str, Tuple[int, int]] = {}
+        pos = 0
+        for (T, S), rels in pair_order.items():
+            ids = [self.rel_index[et] for et in rels]
+            self.jobs[T].append(PairJob(T, S, rels, ids, [edge_index_dict[et] for et in rels],
+                                        num_nodes[S], num_nodes[T]))
+        for T in dst_order:
+            n = sum(j.R for j in self.jobs[T])
+            self.rel_range[T] = (pos, pos + n)
+            pos += n
+        self.n_edges = sum(j.n_edges for js in self.jobs.values() for j in js)
+        self._tensors = [edge_index_dict[et] for et in self.edge_types]   # identity anchors for the cache
+        self._versions = [t._version for t in self._tensors]
+
+    def matches(self, edge_index_dict, num_nodes, conv_keys) -> bool:
+        ets = [et for et in edge_index_dict if (conv_keys is None or et in conv_keys)
+               and et[0] in num_nodes and et[2] in num_nodes]
+        if ets != self.edge_types or num_nodes != self.num_nodes:
+            return False
+        return all(edge_index_dict[et] is t and t._version == v
+                   for et, t, v in zip(self.edge_types, self._tensors, self._versions))
+
+
+_CACHE: List[LayerPlan] = []
+_CACHE_SIZE = 2
+plan_builds = 0
+
+
+def get_plan(edge_index_dict, num_nodes: Dict[str, int], conv_keys=None) -> LayerPlan:
+    """Plans are cached on tensor identity (+ in-place version), most recent first."""
+    global plan_builds
+    for i, p in enumerate(_CACHE):
+        if p.matches(edge_index_dict, num_nodes, conv_keys):
+            if i:
+                _CACHE.insert(0, _CACHE.pop(i))
+            return p
+    for et, ei in edge_index_dict.items():
+        if ei.dtype != torch.int64 or ei.dim() != 2 or ei.size(0) != 2:
+            raise ValueError(f"edge_index of {et} must be int64 [2, E], got {ei.dtype} {tuple(ei.shape)}")
+    p = LayerPlan(edge_index_dict, num_nodes, conv_keys)
+    plan_builds += 1
+    _CACHE.insert(0, p)
+    del _CACHE[_CACHE_SIZE:]
+    return p
+
+
+def clear_plan_cache():
+    _CACHE.clear()
