@@ -43,6 +43,7 @@ enum {
 KGB_API int kgb_version(void);            /* MAJOR*10000 + MINOR*100 + PATCH */
 KGB_API int kgb_sm_arch(void);            /* 100 : compiled for sm_100a only */
 KGB_API const char* kgb_last_error(void); /* thread-local, never NULL */
+KGB_API long long kgb_launch_count(void); /* kernels launched by this library so far (process-wide) */
 
 /* ---- graph bookkeeping ------------------------------------------------------------ */
 /* COO (PyG edge_index [2,E] int64, unsorted, duplicates allowed; kgwas/model.py:53
@@ -74,8 +75,9 @@ KGB_API int kgb_csr_heavy_fill(const int32_t* rowptr, int32_t n_rows, int32_t se
                        void* workspace, size_t workspace_bytes, kgb_stream_t stream);
 
 /* ---- segmented gather-reduce (the message-passing core) --------------------------- */
-/* y[i,:] = act( beta*y[i,:] + sum_{j in [rowptr[i], rowptr[i+1])} w_j * x[col[j], :] )
- *   w_j = ew ? ew[wperm ? wperm[j] : j] : 1          rowsum2[i] = sum_j ew2[wperm ? wperm[j] : j]
+/* y[i,:] = act( beta*y[i,:] + bias + sum_{j in [rowptr[i], rowptr[i+1])} w_j * x[col[j], :] )
+ *   w_j = ew ? ew[wperm ? wperm[j] : j] : 1
+ *   rowsum2[i*bins + col[j] % bins] += ew2[wperm ? wperm[j] : j]      (bins >= 1; optional)
  * One pass: gather -> weighted segmented reduce -> write; no [E,h] message tensor, no atomics
  * on the data path.  Replaces index_select + scatter_add(/mean) of SAGEConv (PyG; instantiated
  * kgwas/model.py:38; mean = precomputed 1/deg edge weights) and `alpha.unsqueeze(-1) * x_j` +
@@ -97,10 +99,11 @@ typedef struct {
 } kgb_csr_t;
 
 KGB_API size_t kgb_spmm_scratch_bytes(int32_t n_hrows, int32_t n_hsegs, int32_t h);
+enum { KGB_MAX_BINS = 8 };
 KGB_API int kgb_spmm(const kgb_csr_t* csr, const float* ew, const int32_t* wperm, const float* ew2,
-                     float* rowsum2, const float* x, int64_t ldx, float* y, int64_t ldy, int32_t h,
-                     float beta, int32_t relu, void* scratch, size_t scratch_bytes,
-                     kgb_stream_t stream);
+                     float* rowsum2, int32_t rowsum2_bins, const float* x, int64_t ldx, float* y,
+                     int64_t ldy, int32_t h, float beta, const float* bias, int32_t relu, void* scratch,
+                     size_t scratch_bytes, kgb_stream_t stream);
 
 /* ---- dense contractions ([nodes x in] . [in x out]) ------------------------------- */
 /* C[M,N] = act( alpha * op(A).op(B) + beta*C + bias[N] )      (row-major, strides in floats)
@@ -139,6 +142,37 @@ KGB_API int kgb_rank_update(const float* a, int64_t lda, int32_t n_slots, const 
 /* out[j] = w[perm[j]]  (edge weights CSR order -> COO order / transposed order) */
 KGB_API int kgb_permute_f32(const float* w, const int32_t* perm, float* out, int64_t n,
                             kgb_stream_t stream);
+
+/* ---- GAT attention (kgwas/conv.py:150-151, 200-228) ------------------------------- */
+/* `groups` is a CSR whose row g = t*n_slots + k is one softmax group (destination node t,
+ * relation slot k) and whose slot order equals the slot order of the job's aggregation CSR.
+ *   u_j = a_src[src_is_node ? col[j]*n_slots + k : col[j]] + a_dst[g]      (conv.py:205)
+ *   z_j = leaky_relu(u_j, negative_slope)                                  (conv.py:217)
+ *   SOFTMAX: alpha_j = exp(z_j/T - max_g) / (sum_g exp(.) + 1e-16)         (conv.py:223)
+ *   SIGMOID: alpha_j = sigmoid(z_j/T)                                      (conv.py:220)
+ *   RAW    : alpha_j = z_j   (`return_raw_attention_weights`)              (conv.py:222)
+ * alpha [E] is written in slot order: it is the edge weight of the following kgb_spmm
+ * (conv.py:227-228), the saved tensor of the backward pass and, permuted by eperm, the
+ * `return_attention_weights` output (conv.py:192-194). */
+enum { KGB_ATT_SOFTMAX = 0, KGB_ATT_SIGMOID = 1, KGB_ATT_RAW = 2 };
+KGB_API size_t kgb_gat_scratch_bytes(int32_t n_hrows, int32_t n_hsegs);
+KGB_API int kgb_gat_alpha(const kgb_csr_t* groups, const float* a_src, const float* a_dst,
+                          int32_t n_slots, int32_t src_is_node, float* alpha, float negative_slope,
+                          float temperature, int32_t mode, void* scratch, size_t scratch_bytes,
+                          kgb_stream_t stream);
+/* out[j] = <xrow[i, :], x[col[j], :]> for every slot j of row i: d(alpha_j) of the weighted
+ * aggregation (dalpha_e = <G[dst(e)], H_s[src(e)]>). */
+KGB_API int kgb_sddmm(const kgb_csr_t* csr, const float* xrow, int64_t ldr, const float* x, int64_t ldx,
+                      int32_t h, float* out, kgb_stream_t stream);
+/* Backward of kgb_gat_alpha:  S_g = sum_j alpha_j dalpha_j
+ *   SOFTMAX dz_j = alpha_j (dalpha_j - S_g)/T | SIGMOID dz_j = alpha_j(1-alpha_j) dalpha_j/T | RAW dz_j = dalpha_j
+ *   du_j = dz_j * (u_j > 0 ? 1 : negative_slope);   da_dst[g] = sum_j du_j;   du [E] in slot order
+ * (d a_src is the row sum of du over the transposed CSR: kgb_spmm's rowsum2). */
+KGB_API int kgb_gat_dsoftmax(const kgb_csr_t* groups, const float* a_src, const float* a_dst,
+                             int32_t n_slots, int32_t src_is_node, const float* alpha,
+                             const float* dalpha, float* du, float* da_dst, float negative_slope,
+                             float temperature, int32_t mode, void* scratch, size_t scratch_bytes,
+                             kgb_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -18,7 +18,13 @@ LIB_PATH = os.path.join(_HERE, "libkgwas_b200.so")
 KGB_NT, KGB_NN, KGB_TN = 0, 1, 2
 
 _lib = None
-launches = 0          # number of kernel-launching C-ABI calls made (bench.py reports it)
+launches = 0          # number of kernel-launching C-ABI calls made
+_prof = None          # bench.py installs a per-launch CUDA-event timer here (None in normal use)
+
+
+def kernel_launch_count() -> int:
+    """Kernels launched by libkgwas_b200 in this process (counted inside the library)."""
+    return int(get_lib().kgb_launch_count())
 
 
 class KgbError(RuntimeError):
@@ -38,13 +44,20 @@ SIGNATURES = {
     "kgb_version": (C.c_int, []),
     "kgb_sm_arch": (C.c_int, []),
     "kgb_last_error": (C.c_char_p, []),
+    "kgb_launch_count": (C.c_longlong, []),
     "kgb_csr_build_workspace_bytes": (_SZ, [_I64, _I64, _I64]),
     "kgb_csr_build": (C.c_int, [_P, _P, _I64, _I64, _I64, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
     "kgb_csr_heavy_count": (C.c_int, [_P, _I32, _I32, _P, _P, _SZ, _P]),
     "kgb_csr_heavy_workspace_bytes": (_SZ, [_I32]),
     "kgb_csr_heavy_fill": (C.c_int, [_P, _I32, _I32, _I32, _I32, _P, _P, _P, _P, _SZ, _P]),
     "kgb_spmm_scratch_bytes": (_SZ, [_I32, _I32, _I32]),
-    "kgb_spmm": (C.c_int, [C.POINTER(CsrStruct), _P, _P, _P, _P, _P, _I64, _P, _I64, _I32, _F, _I32, _P, _SZ, _P]),
+    "kgb_spmm": (C.c_int, [C.POINTER(CsrStruct), _P, _P, _P, _P, _I32, _P, _I64, _P, _I64, _I32, _F, _P, _I32, _P, _SZ,
+                           _P]),
+    "kgb_gat_scratch_bytes": (_SZ, [_I32, _I32]),
+    "kgb_gat_alpha": (C.c_int, [C.POINTER(CsrStruct), _P, _P, _I32, _I32, _P, _F, _F, _I32, _P, _SZ, _P]),
+    "kgb_sddmm": (C.c_int, [C.POINTER(CsrStruct), _P, _I64, _P, _I64, _I32, _P, _P]),
+    "kgb_gat_dsoftmax": (C.c_int, [C.POINTER(CsrStruct), _P, _P, _I32, _I32, _P, _P, _P, _P, _F, _F, _I32, _P, _SZ,
+                                   _P]),
     "kgb_gemm_workspace_bytes": (_SZ, [_I32, _I64, _I64, _I64]),
     "kgb_gemm": (C.c_int, [_I32, _P, _I64, _P, _I64, _P, _I64, _I64, _I64, _I64, _F, _F, _P, _I32, _P, _SZ, _P]),
     "kgb_relu_bwd": (C.c_int, [_P, _P, _P, _I64, _P]),
@@ -181,16 +194,18 @@ def csr_build(src: torch.Tensor, dst: torch.Tensor, n_src: int, n_dst: int, tran
 
 
 def spmm(csr: Csr, x: torch.Tensor, y: torch.Tensor, h: int, *, ew=None, wperm=None, ew2=None, rowsum2=None,
-         beta: float = 0.0, relu: bool = False):
-    """y[i,:h] = act(beta*y[i,:h] + sum_j w_j x[col_j,:h]).  x / y are 2-D views with row strides."""
-    _need_cuda(x, y, ew, wperm, ew2, rowsum2)
+         bins: int = 1, beta: float = 0.0, bias=None, relu: bool = False):
+    """y[i,:h] = act(beta*y[i,:h] + bias + sum_j w_j x[col_j,:h]).  x / y are 2-D views with row strides."""
+    _need_cuda(x, y, ew, wperm, ew2, rowsum2, bias)
     _f32c(x, "spmm x"); _f32c(y, "spmm y")
     if csr.n_rows == 0:
         return y
     if csr.n_edges == 0:
         if beta == 0.0:
             y[:, :h].zero_()
-        elif relu:
+        if bias is not None:
+            y[:, :h].add_(bias)
+        if relu:
             y[:, :h].clamp_(min=0)
         if rowsum2 is not None:
             rowsum2.zero_()
@@ -198,9 +213,13 @@ def spmm(csr: Csr, x: torch.Tensor, y: torch.Tensor, h: int, *, ew=None, wperm=N
     scratch, nbytes = csr.scratch(h)
     global launches
     launches += 1
-    _check(get_lib().kgb_spmm(C.byref(csr.struct), _ptr(ew), _ptr(wperm), _ptr(ew2), _ptr(rowsum2), _ptr(x),
-                              x.stride(0), _ptr(y), y.stride(0), h, beta, int(relu), _ptr(scratch), nbytes,
-                              _stream()), "kgb_spmm")
+    if _prof is not None:
+        _prof.begin("spmm", csr, h, beta)
+    _check(get_lib().kgb_spmm(C.byref(csr.struct), _ptr(ew), _ptr(wperm), _ptr(ew2), _ptr(rowsum2), bins, _ptr(x),
+                              x.stride(0), _ptr(y), y.stride(0), h, beta, _ptr(bias), int(relu), _ptr(scratch),
+                              nbytes, _stream()), "kgb_spmm")
+    if _prof is not None:
+        _prof.end()
     return y
 
 
@@ -292,3 +311,67 @@ def permute_f32(w: torch.Tensor, perm: torch.Tensor, out: Optional[torch.Tensor]
     launches += 1
     _check(get_lib().kgb_permute_f32(_ptr(w), _ptr(perm), _ptr(out), perm.numel(), _stream()), "kgb_permute_f32")
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# GAT edge kernels
+# ---------------------------------------------------------------------------------------------
+
+ATT_SOFTMAX, ATT_SIGMOID, ATT_RAW = 0, 1, 2
+
+
+def _gat_scratch(groups: Csr):
+    if groups.n_hsegs == 0:
+        return None, 0
+    if "gat" not in groups._scratch:
+        nbytes = get_lib().kgb_gat_scratch_bytes(groups.n_hrows, groups.n_hsegs)
+        groups._scratch["gat"] = torch.zeros(nbytes, dtype=torch.uint8, device=groups.rowptr.device)
+    s = groups._scratch["gat"]
+    return s, s.numel()
+
+
+def gat_alpha(groups: Csr, a_src, a_dst, n_slots: int, src_is_node: bool, alpha, slope: float, temperature: float,
+              mode: int):
+    _need_cuda(a_src, a_dst, alpha)
+    if groups.n_edges == 0:
+        return alpha
+    scratch, nbytes = _gat_scratch(groups)
+    global launches
+    launches += 1
+    _check(get_lib().kgb_gat_alpha(C.byref(groups.struct), _ptr(a_src), _ptr(a_dst), n_slots, int(src_is_node),
+                                   _ptr(alpha), slope, temperature, mode, _ptr(scratch), nbytes, _stream()),
+           "kgb_gat_alpha")
+    return alpha
+
+
+def sddmm(csr: Csr, xrow, x, h: int, out):
+    _need_cuda(xrow, x, out)
+    _f32c(xrow, "sddmm xrow"); _f32c(x, "sddmm x")
+    if csr.n_edges == 0:
+        return out
+    global launches
+    launches += 1
+    if _prof is not None:
+        _prof.begin("sddmm", csr, h, 0.0)
+    _check(get_lib().kgb_sddmm(C.byref(csr.struct), _ptr(xrow), xrow.stride(0), _ptr(x), x.stride(0), h, _ptr(out),
+                               _stream()), "kgb_sddmm")
+    if _prof is not None:
+        _prof.end()
+    return out
+
+
+def gat_dsoftmax(groups: Csr, a_src, a_dst, n_slots: int, src_is_node: bool, alpha, dalpha, du, da_dst, slope: float,
+                 temperature: float, mode: int):
+    _need_cuda(a_src, a_dst, alpha, dalpha, du, da_dst)
+    if groups.n_rows == 0:
+        return du, da_dst
+    if groups.n_edges == 0:
+        da_dst.zero_()
+        return du, da_dst
+    scratch, nbytes = _gat_scratch(groups)
+    global launches
+    launches += 1
+    _check(get_lib().kgb_gat_dsoftmax(C.byref(groups.struct), _ptr(a_src), _ptr(a_dst), n_slots, int(src_is_node),
+                                      _ptr(alpha), _ptr(dalpha), _ptr(du), _ptr(da_dst), slope, temperature, mode,
+                                      _ptr(scratch), nbytes, _stream()), "kgb_gat_dsoftmax")
+    return du, da_dst

@@ -1,6 +1,8 @@
 // C-ABI glue: library identity, error text, GEMM dispatch.
 #include <stdarg.h>
 
+#include <atomic>
+
 #include "kgb_common.cuh"
 
 #define KGB_VERSION_MAJOR 0
@@ -13,6 +15,8 @@ char* err_buf() {
   static thread_local char buf[512] = "";
   return buf;
 }
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 void set_error(const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
@@ -37,6 +41,7 @@ using namespace kgb;
 extern "C" int kgb_version(void) { return KGB_VERSION_MAJOR * 10000 + KGB_VERSION_MINOR * 100 + KGB_VERSION_PATCH; }
 extern "C" int kgb_sm_arch(void) { return 100; }
 extern "C" const char* kgb_last_error(void) { return err_buf(); }
+extern "C" long long kgb_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 extern "C" size_t kgb_gemm_workspace_bytes(int32_t layout, int64_t m, int64_t n, int64_t k) {
   size_t a = gemm_ffma_workspace_bytes(layout, m, n, k);

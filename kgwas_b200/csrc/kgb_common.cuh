@@ -15,6 +15,7 @@ constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
 // thread-local error text behind kgb_last_error()
 char* err_buf();
 void set_error(const char* fmt, ...);
+void count_launch();  // every kernel this library launches bumps kgb_launch_count()
 
 #define KGB_CUDA_OK(expr)                                                              \
   do {                                                                                 \
@@ -35,6 +36,7 @@ void set_error(const char* fmt, ...);
 
 #define KGB_LAUNCH_OK()                                                                  \
   do {                                                                                   \
+    kgb::count_launch();                                                                 \
     cudaError_t _e = cudaGetLastError();                                                 \
     if (_e != cudaSuccess) {                                                             \
       kgb::set_error("%s:%d kernel launch -> %s", __FILE__, __LINE__, cudaGetErrorString(_e)); \

@@ -16,11 +16,23 @@ constexpr int kUnroll = 4;
 struct EdgeW {            // per-edge scalars riding along the gather
   const float* ew;        // weight of the gathered row (NULL -> 1)
   const int32_t* wperm;   // weights are indexed ew[wperm[slot]] when non-NULL (transposed CSR)
-  const float* ew2;       // second scalar, only row-summed (NULL -> unused)
+  const float* ew2;       // second scalar, only row-summed into `bins` bins by col % bins (NULL -> unused)
+  int bins;
+};
+struct Sum2 {
+  float v[KGB_MAX_BINS];
+  __device__ __forceinline__ void zero() {
+#pragma unroll
+    for (int b = 0; b < KGB_MAX_BINS; ++b) v[b] = 0.f;
+  }
+  __device__ __forceinline__ void add(int bin, float x) {
+#pragma unroll
+    for (int b = 0; b < KGB_MAX_BINS; ++b) v[b] += (b == bin) ? x : 0.f;
+  }
 };
 
 template <int H>
-__device__ __forceinline__ void gather_accumulate(RowVec<H>& acc, float& sum2, const int32_t* __restrict__ col,
+__device__ __forceinline__ void gather_accumulate(RowVec<H>& acc, Sum2& sum2, const int32_t* __restrict__ col,
                                                   const EdgeW& e, const float* __restrict__ x,
                                                   int64_t ldx, int start, int end, int lane) {
   for (int base = start; base < end; base += kWarp) {
@@ -31,7 +43,7 @@ __device__ __forceinline__ void gather_accumulate(RowVec<H>& acc, float& sum2, c
       c = __ldg(col + base + lane);
       const int wi = e.wperm ? __ldg(e.wperm + base + lane) : base + lane;
       w = e.ew ? __ldg(e.ew + wi) : 1.f;
-      if (e.ew2) sum2 += __ldg(e.ew2 + wi);
+      if (e.ew2) sum2.add(e.bins > 1 ? c % e.bins : 0, __ldg(e.ew2 + wi));
     }
     int j = 0;
     for (; j + kUnroll <= n; j += kUnroll) {
@@ -57,9 +69,14 @@ __device__ __forceinline__ void gather_accumulate(RowVec<H>& acc, float& sum2, c
 }
 
 template <int H>
-__device__ __forceinline__ void write_row(const RowVec<H>& acc, float* __restrict__ yrow, float beta, int relu,
-                                          int lane) {
+__device__ __forceinline__ void write_row(const RowVec<H>& acc, float* __restrict__ yrow, float beta,
+                                          const float* __restrict__ bias, int relu, int lane) {
   RowVec<H> out = acc;
+  if (bias) {
+    RowVec<H> bv;
+    bv.load(bias, lane);
+    out.add(bv);
+  }
   if (beta != 0.f) {
     RowVec<H> old;
     old.load_plain(yrow, lane);
@@ -77,7 +94,7 @@ __device__ __forceinline__ void write_row(const RowVec<H>& acc, float* __restric
 template <int H>
 __global__ void __launch_bounds__(kSpmmThreads)
 k_spmm(kgb_csr_t g, EdgeW e, const float* __restrict__ x, int64_t ldx, float* __restrict__ y, int64_t ldy, float beta,
-       int relu, float* __restrict__ rowsum2, float* __restrict__ partial, float* __restrict__ partial2,
+       const float* __restrict__ bias, int relu, float* __restrict__ rowsum2, float* __restrict__ partial, float* __restrict__ partial2,
        int32_t* __restrict__ ticket) {
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -94,12 +111,18 @@ k_spmm(kgb_csr_t g, EdgeW e, const float* __restrict__ x, int64_t ldx, float* __
       const int end = min(re, start + g.seg_len);
       RowVec<H> acc;
       acc.zero();
-      float s2 = 0.f;
+      Sum2 s2;
+      s2.zero();
       gather_accumulate<H>(acc, s2, g.col, e, x, ldx, start, end, lane);
       acc.store(partial + (int64_t)seg * H, lane);
       if (rowsum2) {
-        s2 = warp_sum(s2);
-        if (lane == 0) partial2[seg] = s2;
+#pragma unroll
+        for (int b = 0; b < KGB_MAX_BINS; ++b) {
+          if (b < e.bins) {
+            const float t2 = warp_sum(s2.v[b]);
+            if (lane == 0) partial2[(int64_t)seg * e.bins + b] = t2;
+          }
+        }
       }
       __threadfence();  // publish this partial before taking a ticket
       int t = 0;
@@ -114,11 +137,11 @@ k_spmm(kgb_csr_t g, EdgeW e, const float* __restrict__ x, int64_t ldx, float* __
           p.load_plain(partial + (int64_t)s * H, lane);
           sum.add(p);
         }
-        write_row<H>(sum, y + (int64_t)row * ldy, beta, relu, lane);
-        if (rowsum2 && lane == 0) {
+        write_row<H>(sum, y + (int64_t)row * ldy, beta, bias, relu, lane);
+        if (rowsum2 && lane < e.bins) {
           float t2 = 0.f;
-          for (int s = seg0; s < seg1; ++s) t2 += __ldcg(partial2 + s);
-          rowsum2[row] = t2;
+          for (int s = seg0; s < seg1; ++s) t2 += __ldcg(partial2 + (int64_t)s * e.bins + lane);
+          rowsum2[(int64_t)row * e.bins + lane] = t2;
         }
         if (lane == 0) ticket[hr] = 0;  // leave the counters clean for the next launch
       }
@@ -128,12 +151,18 @@ k_spmm(kgb_csr_t g, EdgeW e, const float* __restrict__ x, int64_t ldx, float* __
       if (end - start > g.seg_len && g.n_hsegs > 0) continue;  // heavy: handled above
       RowVec<H> acc;
       acc.zero();
-      float s2 = 0.f;
+      Sum2 s2;
+      s2.zero();
       gather_accumulate<H>(acc, s2, g.col, e, x, ldx, start, end, lane);
-      write_row<H>(acc, y + (int64_t)row * ldy, beta, relu, lane);
+      write_row<H>(acc, y + (int64_t)row * ldy, beta, bias, relu, lane);
       if (rowsum2) {
-        s2 = warp_sum(s2);
-        if (lane == 0) rowsum2[row] = s2;
+#pragma unroll
+        for (int b = 0; b < KGB_MAX_BINS; ++b) {
+          if (b < e.bins) {
+            const float t2 = warp_sum(s2.v[b]);
+            if (lane == 0) rowsum2[(int64_t)row * e.bins + b] = t2;
+          }
+        }
       }
     }
   }
@@ -160,13 +189,13 @@ int check_csr(const kgb_csr_t* g, const char* who) {
 using namespace kgb;
 
 extern "C" size_t kgb_spmm_scratch_bytes(int32_t n_hrows, int32_t n_hsegs, int32_t h) {
-  return align_up((size_t)n_hsegs * h * sizeof(float), 256) + align_up((size_t)n_hsegs * sizeof(float), 256) +
+  return align_up((size_t)n_hsegs * h * sizeof(float), 256) + align_up((size_t)n_hsegs * KGB_MAX_BINS * sizeof(float), 256) +
          align_up((size_t)n_hrows * sizeof(int32_t), 256) + 256;
 }
 
 extern "C" int kgb_spmm(const kgb_csr_t* csr, const float* ew, const int32_t* wperm, const float* ew2, float* rowsum2,
-                        const float* x, int64_t ldx, float* y, int64_t ldy, int32_t h, float beta, int32_t relu,
-                        void* scratch, size_t scratch_bytes, kgb_stream_t stream_) {
+                        int32_t rowsum2_bins, const float* x, int64_t ldx, float* y, int64_t ldy, int32_t h, float beta,
+                        const float* bias, int32_t relu, void* scratch, size_t scratch_bytes, kgb_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (int rc = check_csr(csr, "spmm")) return rc;
   if (csr->n_rows == 0) return KGB_OK;
@@ -174,6 +203,8 @@ extern "C" int kgb_spmm(const kgb_csr_t* csr, const float* ew, const int32_t* wp
   KGB_REQUIRE(ldx >= h && ldy >= h && ldx % 4 == 0 && ldy % 4 == 0, "spmm: strides must be >= h and multiples of 4");
   KGB_REQUIRE(aligned16(x) && aligned16(y), "spmm: x/y must be 16-byte aligned");
   KGB_REQUIRE((ew2 == nullptr) == (rowsum2 == nullptr), "spmm: ew2 and rowsum2 go together");
+  KGB_REQUIRE(!ew2 || (rowsum2_bins >= 1 && rowsum2_bins <= KGB_MAX_BINS), "spmm: rowsum2_bins must be in [1, %d]", KGB_MAX_BINS);
+  KGB_REQUIRE(!bias || aligned16(bias), "spmm: bias must be 16-byte aligned");
   float* partial = nullptr;
   float* partial2 = nullptr;
   int32_t* ticket = nullptr;
@@ -184,12 +215,12 @@ extern "C" int kgb_spmm(const kgb_csr_t* csr, const float* ew, const int32_t* wp
     }
     Carver ws(scratch);
     ticket = ws.take<int32_t>(csr->n_hrows);  // counters first: caller zeroes them once
-    partial2 = ws.take<float>((size_t)csr->n_hsegs);
+    partial2 = ws.take<float>((size_t)csr->n_hsegs * KGB_MAX_BINS);
     partial = ws.take<float>((size_t)csr->n_hsegs * h);
   }
-  const EdgeW e{ew, wperm, ew2};
+  const EdgeW e{ew, wperm, ew2, ew2 ? rowsum2_bins : 1};
   const unsigned grid = spmm_grid((int64_t)csr->n_hsegs + csr->n_rows);
-  KGB_DISPATCH_H(h, (k_spmm<H><<<grid, kSpmmThreads, 0, stream>>>(*csr, e, x, ldx, y, ldy, beta, relu, rowsum2, partial, partial2,
+  KGB_DISPATCH_H(h, (k_spmm<H><<<grid, kSpmmThreads, 0, stream>>>(*csr, e, x, ldx, y, ldy, beta, bias, relu, rowsum2, partial, partial2,
                                                                ticket)));
   KGB_LAUNCH_OK();
   return KGB_OK;

@@ -68,7 +68,13 @@ class HeteroGNN(nn.Module):
 
     def forward(self, x_dict, edge_index_dict, batch_size, genotype=None, return_h=False,
                 return_attention_weights=False):
-        x_dict = self.encode(x_dict)
+        return self.forward_from_hidden(self.encode(x_dict), edge_index_dict, batch_size, return_h,
+                                        return_attention_weights)
+
+    def forward_from_hidden(self, x_dict, edge_index_dict, batch_size, return_h=False,
+                            return_attention_weights=False):
+        """model.py:62-86 on already-projected ``[N, hidden]`` features: L x (HeteroConv -> ReLU),
+        head, slice.  This is the region the edges-aggregated/s metric is defined on."""
         attention_all_layers = []
         for conv in self.convs:
             if return_attention_weights:                                   # model.py:65-72

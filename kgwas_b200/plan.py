@@ -26,6 +26,7 @@ import torch
 from . import _lib
 
 EdgeType = Tuple[str, str, str]
+MAX_SLOTS = 8      # KGB_MAX_BINS of the C ABI
 
 
 class PairJob:
@@ -62,7 +63,15 @@ class PairJob:
             self.group_rowptr = gp.to(torch.int32)
         else:
             self.group_rowptr = self.csr.rowptr
-        self.group_of_slot = group[self.eperm.long()].to(torch.int32).contiguous()
+        self._gcsr = None
+
+    @property
+    def gcsr(self) -> "_lib.Csr":
+        """CSR whose rows are the softmax groups (t, k), over the same slot order as ``csr``."""
+        if self._gcsr is None:
+            self._gcsr = self.csr if self.mode == "af" else _lib.Csr(self.group_rowptr, self.csr.col,
+                                                                      self.n_dst * self.R, self.csr.n_cols)
+        return self._gcsr
 
     def __repr__(self):
         return (f"PairJob({self.src_type}->{self.dst_type}, R={self.R}, mode={self.mode}, E={self.n_edges}, "
@@ -95,10 +104,12 @@ class LayerPlan:
         self.jobs: Dict[str, List[PairJob]] = {T: [] for T in dst_order}
         self.rel_range: Dict[str, Tuple[int, int]] = {}
         pos = 0
-        for (T, S), rels in pair_order.items():
-            ids = [self.rel_index[et] for et in rels]
-            self.jobs[T].append(PairJob(T, S, rels, ids, [edge_index_dict[et] for et in rels],
-                                        num_nodes[S], num_nodes[T]))
+        for (T, S), rels_all in pair_order.items():
+            for c in range(0, len(rels_all), MAX_SLOTS):          # at most MAX_SLOTS relations per job
+                rels = rels_all[c:c + MAX_SLOTS]
+                ids = [self.rel_index[et] for et in rels]
+                self.jobs[T].append(PairJob(T, S, rels, ids, [edge_index_dict[et] for et in rels],
+                                            num_nodes[S], num_nodes[T]))
         for T in dst_order:
             n = sum(j.R for j in self.jobs[T])
             self.rel_range[T] = (pos, pos + n)

@@ -1,0 +1,185 @@
+"""GPU parity: GAT edge kernels and the drop-in GAT modules vs the CPU oracle (kgwas/conv.py restated)."""
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import kgwas_oracle as O
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-4
+
+
+def _rel_err(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return ((a - b).abs().max() / b.abs().max().clamp(min=1e-12)).item()
+
+
+@pytest.mark.parametrize("mode,temperature", [(0, 1.0), (0, 0.5), (1, 2.0), (2, 1.0)])
+def test_gat_alpha_and_backward_kernels(cuda, mode, temperature):
+    """kgb_gat_alpha / kgb_sddmm / kgb_gat_dsoftmax on one bipartite relation with a hub
+    destination (heavy-segment path) vs torch autograd in fp64."""
+    from kgwas_b200 import _lib
+    rng = np.random.default_rng(7)
+    n_src, n_dst, e, h = 900, 60, 40000, 64
+    src = rng.integers(0, n_src, e)
+    dst = rng.integers(0, n_dst, e)
+    dst[: e // 2] = 3
+    dst[dst == 7] = 8                                                     # empty group
+    s, d = torch.from_numpy(src).to(cuda), torch.from_numpy(dst).to(cuda)
+    csr, eperm, tcsr, t_eperm = _lib.csr_build(s, d, n_src, n_dst, seg_len=64)
+    assert csr.n_hsegs > 0
+    a_src = torch.randn(n_src, 1, device=cuda)
+    a_dst = torch.randn(n_dst, 1, device=cuda)
+    x = torch.randn(n_src, h, device=cuda)
+    g = torch.randn(n_dst, h, device=cuda)
+    alpha = torch.empty(e, device=cuda)
+    _lib.gat_alpha(csr, a_src, a_dst, 1, True, alpha, 0.2, temperature, mode)
+    # fp64 reference
+    as64, ad64, x64 = a_src.double().requires_grad_(), a_dst.double().requires_grad_(), x.double().requires_grad_()
+    z = torch.nn.functional.leaky_relu(as64[s, 0] + ad64[d, 0], 0.2)
+    if mode == 0:
+        ref_alpha = O.pyg_softmax(z / temperature, d, n_dst)
+    elif mode == 1:
+        ref_alpha = torch.sigmoid(z / temperature)
+    else:
+        ref_alpha = z
+    alpha_coo = torch.empty_like(alpha)
+    alpha_coo[eperm.long()] = alpha
+    assert torch.allclose(alpha_coo.double(), ref_alpha, rtol=1e-4, atol=1e-6)
+    out_ref = torch.zeros(n_dst, h, dtype=torch.float64, device=cuda).index_add_(0, d, ref_alpha[:, None] * x64[s])
+    (out_ref * g.double()).sum().backward()
+    dalpha = torch.empty(e, device=cuda)
+    _lib.sddmm(csr, g, x, h, dalpha)
+    ref_dalpha = (g.double()[d] * x.double()[s]).sum(-1)
+    dalpha_coo = torch.empty_like(dalpha)
+    dalpha_coo[eperm.long()] = dalpha
+    assert torch.allclose(dalpha_coo.double(), ref_dalpha, rtol=1e-5, atol=1e-4)
+    du = torch.empty(e, device=cuda)
+    da_dst = torch.full((n_dst, 1), 9.0, device=cuda)
+    for _ in range(2):                                                     # tickets must come back clean
+        _lib.gat_dsoftmax(csr, a_src, a_dst, 1, True, alpha, dalpha, du, da_dst, 0.2, temperature, mode)
+        assert torch.allclose(da_dst.double(), ad64.grad, rtol=1e-3, atol=2e-4), (da_dst.double() - ad64.grad).abs().max()
+    dx = torch.empty(n_src, h, device=cuda)
+    da_src = torch.empty(n_src, 1, device=cuda)
+    _lib.spmm(tcsr, g, dx, h, ew=alpha, wperm=t_eperm, ew2=du, rowsum2=da_src, bins=1)
+    assert torch.allclose(da_src.double(), as64.grad, rtol=1e-3, atol=2e-4)
+    assert torch.allclose(dx.double(), x64.grad, rtol=1e-4, atol=1e-4)
+
+
+def _gat_pair(data, h, aggr="sum", layers=2, seed=0, no_relu=True, **kw):
+    import kgwas_b200
+    torch.manual_seed(seed)
+    ref = O.HeteroGNN(data, h, 1, layers, "GAT", aggr, h, h, h, 1, no_relu=no_relu)
+    ref({k: v.clone() for k, v in data.x_dict.items()}, data.edge_index_dict, 4)
+    with torch.no_grad():                       # biases are zero-initialised: make them matter
+        for n, p in ref.named_parameters():
+            if n.endswith(".bias") and ".convs." in n:
+                p.normal_(0, 0.1)
+    ours = kgwas_b200.HeteroGNN(data, h, 1, layers, "GAT", aggr, h, h, h, 1, no_relu=no_relu)
+    ours.load_state_dict(ref.state_dict())
+    return ref, ours
+
+
+@pytest.mark.parametrize("h,scale,aggr", [(32, 0.002, "sum"), (128, 0.004, "sum"), (64, 0.003, "mean"), (256, 0.002, "sum")])
+def test_hetero_gat_forward_backward(cuda, h, scale, aggr):
+    from kgwas_b200 import make_synth_kg
+    data = make_synth_kg(scale=scale, seed=5, hidden=h)
+    ref, ours = _gat_pair(data, h, aggr)
+    ref64 = copy.deepcopy(ref).double()
+    ours = ours.to(cuda)
+    gdata = data.to(cuda)
+    bs = 150
+    w = torch.rand(bs, dtype=torch.float64)
+    yt = torch.randn(bs)
+
+    def run(model, x_dict, ei, dev, dt):
+        out = model(x_dict, ei, bs).reshape(-1)
+        return out, torch.mean(w.to(dev) * (out - yt.to(dev, dt)) ** 2)
+
+    out_r, loss_r = run(ref, {k: v.clone() for k, v in data.x_dict.items()}, data.edge_index_dict, "cpu", torch.float32)
+    out_64, loss_64 = run(ref64, {k: v.double() for k, v in data.x_dict.items()}, data.edge_index_dict, "cpu", torch.float64)
+    out_g, loss_g = run(ours, gdata.x_dict, gdata.edge_index_dict, cuda, torch.float32)
+    loss_r.backward(); loss_64.backward(); loss_g.backward()
+    torch.cuda.synchronize()
+    assert _rel_err(out_g, out_64) < RTOL, (_rel_err(out_g, out_64), _rel_err(out_r, out_64))
+    assert _rel_err(out_g, out_r) < RTOL
+    p_ref, p_64, p_g = dict(ref.named_parameters()), dict(ref64.named_parameters()), dict(ours.named_parameters())
+    assert p_ref.keys() == p_g.keys()
+    for k in p_ref:
+        lazy = isinstance(p_ref[k], torch.nn.parameter.UninitializedParameter)
+        assert lazy == isinstance(p_g[k], torch.nn.parameter.UninitializedParameter), k
+        if lazy:
+            continue
+        if p_ref[k].grad is None:
+            assert p_g[k].grad is None, k
+            continue
+        assert p_g[k].grad is not None, k
+        if p_64[k].grad.abs().max().item() == 0:
+            continue
+        err = _rel_err(p_g[k].grad, p_64[k].grad)
+        assert err < 2e-3, (k, err, _rel_err(p_ref[k].grad, p_64[k].grad))
+
+
+def test_gat_microcases(cuda):
+    """isolated destination -> bias; duplicate edges counted twice in the softmax;
+    single-tensor path (H_t = H_s); temperature / sigmoid / raw modes; returned attention in COO order."""
+    import kgwas_b200
+    h = 32
+    torch.manual_seed(2)
+    x_src, x_dst = torch.randn(4, h), torch.randn(3, h)
+    ei = torch.tensor([[0, 0, 1, 3], [1, 1, 1, 2]])
+    for kwargs in ({}, {"temperature": 0.5}, {"sigmoid_gat": True, "temperature": 2.0}):
+        ref = O.GATConv((h, h), h, add_self_loops=False, **kwargs)
+        ref.lin_src(x_src); ref.lin_dst(x_dst)
+        with torch.no_grad():
+            ref.bias.normal_()
+        ours = kgwas_b200.GATConv((h, h), h, add_self_loops=False, **kwargs)
+        ours.load_state_dict(ref.state_dict())
+        ours = ours.to(cuda)
+        for raw in (None, True):
+            o_r, (ei_r, a_r) = ref((x_src, x_dst), ei, return_attention_weights=True, return_raw_attention_weights=raw)
+            o_g, (ei_g, a_g) = ours((x_src.to(cuda), x_dst.to(cuda)), ei.to(cuda), return_attention_weights=True,
+                                    return_raw_attention_weights=raw)
+            assert torch.equal(ei_g.cpu(), ei_r) and a_g.shape == a_r.shape == (4, 1)
+            assert torch.allclose(a_g.cpu(), a_r, rtol=1e-4, atol=1e-6)
+            assert torch.allclose(o_g.cpu(), o_r, rtol=1e-4, atol=1e-5)
+            assert torch.allclose(o_g[0].cpu(), ref.bias, atol=1e-6)                 # isolated destination
+    # single-tensor path
+    ref = O.GATConv(h, h, add_self_loops=False)
+    ours = kgwas_b200.GATConv(h, h, add_self_loops=False)
+    ours.load_state_dict(ref.state_dict())
+    ours = ours.to(cuda)
+    x = torch.randn(5, h)
+    ei2 = torch.tensor([[0, 1, 2, 2, 4], [1, 2, 2, 0, 0]])
+    assert torch.allclose(ours(x.to(cuda), ei2.to(cuda)).cpu(), ref(x, ei2), rtol=1e-4, atol=1e-5)
+
+
+def test_hetero_gat_attention_export(cuda):
+    """return_attention_weights / return_raw_attention_weights plumbing (kgwas/model.py:65-72,
+    kgwas/utils.py:453-458) on a graph where every destination type has >= 2 relations."""
+    import kgwas_b200
+    h = 32
+    torch.manual_seed(11)
+    ets = [("a", "r1", "b"), ("a", "r2", "b"), ("b", "r3", "b"), ("b", "r4", "a"), ("a", "r5", "a")]
+    n = {"a": 40, "b": 25}
+    ei = {et: torch.stack([torch.randint(0, n[et[0]], (150,)), torch.randint(0, n[et[2]], (150,))]) for et in ets}
+    x = {k: torch.randn(v, h) for k, v in n.items()}
+    ref = O.HeteroConv({et: O.GATConv((-1, -1), h, add_self_loops=False) for et in ets}, aggr="sum")
+    ref(x, ei)
+    ours = kgwas_b200.HeteroConv({et: kgwas_b200.GATConv((-1, -1), h, add_self_loops=False) for et in ets}, aggr="sum")
+    ours.load_state_dict(ref.state_dict())
+    ours = ours.to(cuda)
+    xg, eig = {k: v.to(cuda) for k, v in x.items()}, {k: v.to(cuda) for k, v in ei.items()}
+    flags = dict(zip(ets, [True] * len(ets)))
+    for extra in ({}, {"return_raw_attention_weights_dict": flags}):
+        o_r = ref(x, ei, return_attention_weights_dict=flags, **extra)
+        o_g = ours(xg, eig, return_attention_weights_dict=flags, **extra)
+        assert o_r.keys() == o_g.keys()
+        for k in o_r:
+            assert _rel_err(o_g[k][0], o_r[k][0]) < RTOL
+            assert len(o_g[k][1]) == len(o_r[k][1])
+            for (ei_g, a_g), (ei_r, a_r) in zip(o_g[k][1], o_r[k][1]):
+                assert torch.equal(ei_g.cpu(), ei_r)
+                assert torch.allclose(a_g.cpu(), a_r, rtol=1e-4, atol=1e-6)
