@@ -253,6 +253,8 @@ def ours(args):
         nonlocal opt
         if opt is not None:
             opt.zero_grad(set_to_none=True)
+        for v in x.values():
+            v.grad = None           # the features stand for the MLP outputs: their gradient is produced, not accumulated
         pred = model.forward_from_hidden(x, ei, n_snp).reshape(-1)
         loss = torch.mean(w_d * (pred - y_d) ** 2)                       # kgwas.py:145
         loss.backward()

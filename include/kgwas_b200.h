@@ -53,11 +53,16 @@ KGB_API long long kgb_launch_count(void); /* kernels launched by this library so
  *   eperm   [E]        original edge id of CSR slot i      (carries GAT alpha back to COO order)
  *   t_rowptr[n_src+1]  t_col[E] = dst of the j-th edge in src-major order
  *   t_eperm [E]        CSR slot of transposed slot j       (weights_csc = weights_csr[t_eperm])
+ * sort_cols != 0: slots of one row are ordered by (source index, original edge id) instead of by
+ * original edge id alone -- heavy rows then sweep the gathered table front to back, which is what
+ * the L2-window scheduling of kgb_spmm relies on.  presort_key (nullable, values in [0, n_src)) replaces
+ * the source index as that in-row ordering key.  The transposed CSR is column-sorted either way.
  * Replaces the index handling inside PyG MessagePassing.propagate / scatter (reached from
  * kgwas/conv.py:182 and kgwas/model.py:74).  Any of the t_* outputs may be NULL (all three). */
 KGB_API size_t kgb_csr_build_workspace_bytes(int64_t n_edges, int64_t n_src, int64_t n_dst);
 KGB_API int kgb_csr_build(const int64_t* src, const int64_t* dst, int64_t n_edges, int64_t n_src,
-                  int64_t n_dst, int32_t* rowptr, int32_t* col, int32_t* eperm,
+                  int64_t n_dst, int32_t sort_cols, const int64_t* presort_key, int32_t* rowptr,
+                  int32_t* col, int32_t* eperm,
                   int32_t* t_rowptr, int32_t* t_col, int32_t* t_eperm, void* workspace,
                   size_t workspace_bytes, kgb_stream_t stream);
 
@@ -66,6 +71,7 @@ KGB_API int kgb_csr_build(const int64_t* src, const int64_t* dst, int64_t n_edge
  *   hrow_id    [n_hrows]    row index of each heavy row (ascending)
  *   hrow_segptr[n_hrows+1]  prefix sum of segments per heavy row
  *   hseg_hrow  [n_hsegs]    heavy-row slot of each segment
+ * (hrow_grpptr of kgb_csr_t is derived from hrow_segptr by the caller)
  * h_counts (HOST, 2 ints) receives {n_hrows, n_hsegs}; this one call synchronises the stream. */
 KGB_API int kgb_csr_heavy_count(const int32_t* rowptr, int32_t n_rows, int32_t seg_len, int32_t* h_counts,
                         void* workspace, size_t workspace_bytes, kgb_stream_t stream);
@@ -96,9 +102,13 @@ typedef struct {
   const int32_t* hrow_id;
   const int32_t* hrow_segptr;
   const int32_t* hseg_hrow;
+  const int32_t* hseg_order; /* nullable: work item i processes segment hseg_order[i] (L2-window scheduling) */
+  const int32_t* hrow_grpptr; /* [n_hrows+1] prefix sum of ceil(segments / KGB_FOLD) per heavy row */
+  int32_t n_hgroups;          /* hrow_grpptr[n_hrows] */
 } kgb_csr_t;
+enum { KGB_FOLD = 64 };       /* partial sums are folded 64 at a time (two levels) by the last finisher */
 
-KGB_API size_t kgb_spmm_scratch_bytes(int32_t n_hrows, int32_t n_hsegs, int32_t h);
+KGB_API size_t kgb_spmm_scratch_bytes(int32_t n_hrows, int32_t n_hsegs, int32_t n_hgroups, int32_t h);
 enum { KGB_MAX_BINS = 8 };
 KGB_API int kgb_spmm(const kgb_csr_t* csr, const float* ew, const int32_t* wperm, const float* ew2,
                      float* rowsum2, int32_t rowsum2_bins, const float* x, int64_t ldx, float* y,

@@ -34,7 +34,8 @@ class KgbError(RuntimeError):
 class CsrStruct(C.Structure):
     _fields_ = [("rowptr", C.c_void_p), ("col", C.c_void_p), ("n_rows", C.c_int32), ("seg_len", C.c_int32),
                 ("n_hrows", C.c_int32), ("n_hsegs", C.c_int32), ("hrow_id", C.c_void_p),
-                ("hrow_segptr", C.c_void_p), ("hseg_hrow", C.c_void_p)]
+                ("hrow_segptr", C.c_void_p), ("hseg_hrow", C.c_void_p), ("hseg_order", C.c_void_p),
+                ("hrow_grpptr", C.c_void_p), ("n_hgroups", C.c_int32)]
 
 
 _P, _I32, _I64, _F, _SZ = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_size_t
@@ -46,11 +47,11 @@ SIGNATURES = {
     "kgb_last_error": (C.c_char_p, []),
     "kgb_launch_count": (C.c_longlong, []),
     "kgb_csr_build_workspace_bytes": (_SZ, [_I64, _I64, _I64]),
-    "kgb_csr_build": (C.c_int, [_P, _P, _I64, _I64, _I64, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
+    "kgb_csr_build": (C.c_int, [_P, _P, _I64, _I64, _I64, _I32, _P, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
     "kgb_csr_heavy_count": (C.c_int, [_P, _I32, _I32, _P, _P, _SZ, _P]),
     "kgb_csr_heavy_workspace_bytes": (_SZ, [_I32]),
     "kgb_csr_heavy_fill": (C.c_int, [_P, _I32, _I32, _I32, _I32, _P, _P, _P, _P, _SZ, _P]),
-    "kgb_spmm_scratch_bytes": (_SZ, [_I32, _I32, _I32]),
+    "kgb_spmm_scratch_bytes": (_SZ, [_I32, _I32, _I32, _I32]),
     "kgb_spmm": (C.c_int, [C.POINTER(CsrStruct), _P, _P, _P, _P, _I32, _P, _I64, _P, _I64, _I32, _F, _P, _I32, _P, _SZ,
                            _P]),
     "kgb_gat_scratch_bytes": (_SZ, [_I32, _I32]),
@@ -112,7 +113,9 @@ def _f32c(t, name):
 # graph bookkeeping
 # ---------------------------------------------------------------------------------------------
 
-SEG_LEN = 256
+SEG_LEN = 64            # edges per heavy-row segment (one warp each)
+FOLD = 64               # KGB_FOLD: partials folded per level
+L2_WINDOW_BYTES = 48 << 20   # gathered-table window the resident warps should share (126 MB L2)
 
 
 class Csr:
@@ -120,12 +123,32 @@ class Csr:
 
     def __init__(self, rowptr, col, n_rows, n_cols, seg_len=SEG_LEN):
         self.rowptr, self.col, self.n_rows, self.n_cols, self.seg_len = rowptr, col, n_rows, n_cols, seg_len
-        self.n_hrows = self.n_hsegs = 0
-        self.hrow_id = self.hrow_segptr = self.hseg_hrow = None
+        self.n_hrows = self.n_hsegs = self.n_hgroups = 0
+        self.hrow_id = self.hrow_segptr = self.hseg_hrow = self.hrow_grpptr = None
         self._scratch = {}
+        self.hseg_order = None
         self._build_heavy()
-        self.struct = CsrStruct(_ptr(rowptr), _ptr(col), n_rows, seg_len, self.n_hrows, self.n_hsegs,
-                                _ptr(self.hrow_id), _ptr(self.hrow_segptr), _ptr(self.hseg_hrow))
+        self._refresh_struct()
+
+    def _refresh_struct(self):
+        self.struct = CsrStruct(_ptr(self.rowptr), _ptr(self.col), self.n_rows, self.seg_len, self.n_hrows,
+                                self.n_hsegs, _ptr(self.hrow_id), _ptr(self.hrow_segptr), _ptr(self.hseg_hrow),
+                                _ptr(self.hseg_order), _ptr(self.hrow_grpptr), self.n_hgroups)
+
+    def schedule_for_l2(self, row_bytes: int, window_bytes: int = L2_WINDOW_BYTES):
+        """Order the heavy segments by the window of the gathered table they read (rows are column-sorted), so
+        that concurrently resident warps gather from the same L2-sized slice instead of sweeping the whole table
+        once per hub row.  No-op when the table fits the window."""
+        if self.n_hsegs == 0 or self.n_cols * row_bytes <= window_bytes:
+            return self
+        window_rows = max(1, window_bytes // row_bytes)
+        hr = self.hseg_hrow.long()
+        seg_in_row = torch.arange(self.n_hsegs, device=hr.device) - self.hrow_segptr.long()[hr]
+        first_slot = self.rowptr.long()[self.hrow_id.long()[hr]] + seg_in_row * self.seg_len
+        key = torch.div(self.col.long()[first_slot], window_rows, rounding_mode="floor")
+        self.hseg_order = torch.argsort(key, stable=True).to(torch.int32)
+        self._refresh_struct()
+        return self
 
     @property
     def n_edges(self):
@@ -150,20 +173,25 @@ class Csr:
         _check(lib.kgb_csr_heavy_fill(_ptr(self.rowptr), self.n_rows, self.seg_len, self.n_hrows, self.n_hsegs,
                                       _ptr(self.hrow_id), _ptr(self.hrow_segptr), _ptr(self.hseg_hrow), _ptr(ws),
                                       ws_bytes, _stream()), "kgb_csr_heavy_fill")
+        nseg = self.hrow_segptr[1:] - self.hrow_segptr[:-1]
+        grp = torch.zeros(self.n_hrows + 1, dtype=torch.int32, device=dev)
+        grp[1:] = torch.cumsum((nseg + FOLD - 1) // FOLD, 0)
+        self.hrow_grpptr = grp
+        self.n_hgroups = int(grp[-1].item())
 
     def scratch(self, h: int):
         """Per-CSR scratch for heavy-row partials (zeroed once; kernels leave the tickets zero)."""
         if self.n_hsegs == 0:
             return None, 0
         if h not in self._scratch:
-            nbytes = get_lib().kgb_spmm_scratch_bytes(self.n_hrows, self.n_hsegs, h)
+            nbytes = get_lib().kgb_spmm_scratch_bytes(self.n_hrows, self.n_hsegs, self.n_hgroups, h)
             self._scratch[h] = torch.zeros(nbytes, dtype=torch.uint8, device=self.rowptr.device)
         s = self._scratch[h]
         return s, s.numel()
 
 
 def csr_build(src: torch.Tensor, dst: torch.Tensor, n_src: int, n_dst: int, transposed: bool = True,
-              seg_len: int = SEG_LEN):
+              seg_len: int = SEG_LEN, sort_cols: bool = False, presort_key: Optional[torch.Tensor] = None):
     """COO (int64) -> (Csr by dst, eperm, Csr by src | None, t_eperm | None) via kgb_csr_build."""
     _need_cuda(src, dst)
     if src.dtype != torch.int64 or dst.dtype != torch.int64:
@@ -180,7 +208,8 @@ def csr_build(src: torch.Tensor, dst: torch.Tensor, n_src: int, n_dst: int, tran
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     global launches
     launches += 1
-    _check(lib.kgb_csr_build(_ptr(src), _ptr(dst), E, n_src, n_dst, _ptr(rowptr), _ptr(col), _ptr(eperm),
+    _check(lib.kgb_csr_build(_ptr(src), _ptr(dst), E, n_src, n_dst, int(sort_cols),
+                             _ptr(presort_key), _ptr(rowptr), _ptr(col), _ptr(eperm),
                              _ptr(t_rowptr), _ptr(t_col), _ptr(t_eperm), _ptr(ws), ws_bytes, _stream()),
            "kgb_csr_build")
     fwd = Csr(rowptr, col, n_dst, n_src, seg_len)

@@ -41,6 +41,13 @@ __global__ void k_gather_cols(const int64_t* __restrict__ other64, const int32_t
   }
 }
 
+// key32[i] = (int32) key64[idx[i]]
+__global__ void k_gather_keys64(const int64_t* __restrict__ key64, const int32_t* __restrict__ idx, int64_t n,
+                                int32_t* __restrict__ key32) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) key32[i] = (int32_t)key64[idx[i]];
+}
+
 // t_col[j] = dst_sorted[t_eperm[j]]
 __global__ void k_gather_i32(const int32_t* __restrict__ table, const int32_t* __restrict__ idx, int64_t n,
                              int32_t* __restrict__ out) {
@@ -76,7 +83,7 @@ extern "C" size_t kgb_csr_build_workspace_bytes(int64_t n_edges, int64_t n_src, 
 }
 
 extern "C" int kgb_csr_build(const int64_t* src, const int64_t* dst, int64_t E, int64_t n_src, int64_t n_dst,
-                             int32_t* rowptr, int32_t* col, int32_t* eperm, int32_t* t_rowptr, int32_t* t_col,
+                             int32_t sort_cols, const int64_t* presort_key, int32_t* rowptr, int32_t* col, int32_t* eperm, int32_t* t_rowptr, int32_t* t_col,
                              int32_t* t_eperm, void* workspace, size_t workspace_bytes, kgb_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   KGB_REQUIRE(E >= 0 && n_src >= 0 && n_dst >= 0, "csr_build: negative size");
@@ -105,8 +112,19 @@ extern "C" int kgb_csr_build(const int64_t* src, const int64_t* dst, int64_t E, 
   const unsigned gE = (unsigned)((E + T - 1) / T);
 
   // ---- by destination -------------------------------------------------------------
-  k_prepare_keys<<<gE, T, 0, stream>>>(dst, E, k0, v0);
-  KGB_LAUNCH_OK();
+  if (sort_cols) {
+    // pre-order the edge ids by source; the stable sort by destination below keeps that order inside a row
+    k_prepare_keys<<<gE, T, 0, stream>>>(presort_key ? presort_key : src, E, k0, v0);
+    KGB_LAUNCH_OK();
+    cub::DoubleBuffer<int32_t> kb(k0, k1), vb(v0, v1);
+    KGB_CUDA_OK(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, kb, vb, (int)E, 0, bits_for(n_src), stream));
+    if (vb.Current() != v0) KGB_CUDA_OK(cudaMemcpyAsync(v0, vb.Current(), E * 4, cudaMemcpyDeviceToDevice, stream));
+    k_gather_keys64<<<gE, T, 0, stream>>>(dst, v0, E, k0);   // k0[i] = dst[v0[i]]
+    KGB_LAUNCH_OK();
+  } else {
+    k_prepare_keys<<<gE, T, 0, stream>>>(dst, E, k0, v0);
+    KGB_LAUNCH_OK();
+  }
   {
     cub::DoubleBuffer<int32_t> kb(k0, k1), vb(v0, v1);
     KGB_CUDA_OK(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, kb, vb, (int)E, 0, bits_for(n_dst), stream));

@@ -71,7 +71,7 @@ k_gat_alpha_a(kgb_csr_t g, AttArgs p, float* __restrict__ alpha, HeavyScratch hs
   const int64_t n_items = (int64_t)g.n_hsegs + g.n_rows;
   for (int64_t item = warp0; item < n_items; item += n_warps) {
     if (item < g.n_hsegs) {
-      const int seg = (int)item;
+      const int seg = g.hseg_order ? __ldg(g.hseg_order + item) : (int)item;
       const int hr = __ldg(g.hseg_hrow + seg);
       const int row = __ldg(g.hrow_id + hr);
       const int seg0 = __ldg(g.hrow_segptr + hr), seg1 = __ldg(g.hrow_segptr + hr + 1);
@@ -91,11 +91,13 @@ k_gat_alpha_a(kgb_csr_t g, AttArgs p, float* __restrict__ alpha, HeavyScratch hs
       t = __shfl_sync(0xffffffffu, t, 0);
       if (t == seg1 - seg0 - 1) {
         __threadfence();
+        float M = -INFINITY;                                  // lanes stride over the segments: fixed mapping
+        for (int q = seg0 + lane; q < seg1; q += 32) M = fmaxf(M, __ldcg(hs.seg_a + q));
+        M = warp_max(M);
+        float L = 0.f;
+        for (int q = seg0 + lane; q < seg1; q += 32) L += __ldcg(hs.seg_b + q) * __expf(__ldcg(hs.seg_a + q) - M);
+        L = warp_sum(L);
         if (lane == 0) {
-          float M = -INFINITY;
-          for (int q = seg0; q < seg1; ++q) M = fmaxf(M, __ldcg(hs.seg_a + q));
-          float L = 0.f;
-          for (int q = seg0; q < seg1; ++q) L += __ldcg(hs.seg_b + q) * __expf(__ldcg(hs.seg_a + q) - M);
           hs.row_a[hr] = M;
           hs.row_b[hr] = L;
           hs.ticket[hr] = 0;
@@ -166,7 +168,7 @@ k_gat_dsoftmax_a(kgb_csr_t g, AttArgs p, const float* __restrict__ alpha, const 
   for (int64_t item = warp0; item < n_items; item += n_warps) {
     if (item < g.n_hsegs) {
       if (p.mode != KGB_ATT_SOFTMAX) continue;  // no group statistic needed: phase B does everything
-      const int seg = (int)item;
+      const int seg = g.hseg_order ? __ldg(g.hseg_order + item) : (int)item;
       const int hr = __ldg(g.hseg_hrow + seg);
       const int row = __ldg(g.hrow_id + hr);
       const int seg0 = __ldg(g.hrow_segptr + hr), seg1 = __ldg(g.hrow_segptr + hr + 1);
@@ -180,9 +182,10 @@ k_gat_dsoftmax_a(kgb_csr_t g, AttArgs p, const float* __restrict__ alpha, const 
       t = __shfl_sync(0xffffffffu, t, 0);
       if (t == seg1 - seg0 - 1) {
         __threadfence();
+        float tot = 0.f;
+        for (int q = seg0 + lane; q < seg1; q += 32) tot += __ldcg(hs.seg_a + q);
+        tot = warp_sum(tot);
         if (lane == 0) {
-          float tot = 0.f;
-          for (int q = seg0; q < seg1; ++q) tot += __ldcg(hs.seg_a + q);
           hs.row_a[hr] = tot;
           hs.ticket[hr] = 0;
         }
@@ -222,9 +225,10 @@ k_gat_dsoftmax_b(kgb_csr_t g, AttArgs p, const float* __restrict__ alpha, const 
     t = __shfl_sync(0xffffffffu, t, 0);
     if (t == seg1 - seg0 - 1) {
       __threadfence();
+      float tot = 0.f;
+      for (int q = seg0 + lane; q < seg1; q += 32) tot += __ldcg(hs.seg_b + q);
+      tot = warp_sum(tot);
       if (lane == 0) {
-        float tot = 0.f;
-        for (int q = seg0; q < seg1; ++q) tot += __ldcg(hs.seg_b + q);
         da_dst[row] = tot;
         hs.ticket[hr] = 0;
       }
@@ -244,7 +248,7 @@ k_sddmm(kgb_csr_t g, const float* __restrict__ xrow, int64_t ldr, const float* _
   for (int64_t item = warp0; item < n_items; item += n_warps) {
     int row, s, e;
     if (item < g.n_hsegs) {
-      const int seg = (int)item;
+      const int seg = g.hseg_order ? __ldg(g.hseg_order + item) : (int)item;
       const int hr = __ldg(g.hseg_hrow + seg);
       row = __ldg(g.hrow_id + hr);
       const int seg0 = __ldg(g.hrow_segptr + hr);

@@ -11,7 +11,7 @@
 namespace kgb {
 
 constexpr int kSpmmThreads = 256;  // 8 warps / CTA
-constexpr int kUnroll = 4;
+constexpr int kUnroll = 8;   // gathers in flight per warp
 
 struct EdgeW {            // per-edge scalars riding along the gather
   const float* ew;        // weight of the gathered row (NULL -> 1)
@@ -90,19 +90,50 @@ __device__ __forceinline__ void write_row(const RowVec<H>& acc, float* __restric
   out.store(yrow, lane);
 }
 
+struct HeavyBufs {
+  int32_t* ticket;    // [n_hrows]    groups finished per heavy row
+  int32_t* ticket1;   // [n_hgroups]  segments finished per group
+  float* partial;     // [n_hsegs, H]
+  float* gpartial;    // [n_hgroups, H]
+  float* partial2;    // [n_hsegs, bins]
+  float* gpartial2;   // [n_hgroups, bins]
+};
+
+// sum of n consecutive H-wide rows written earlier in this kernel (coherent loads), 8 in flight, index order
+template <int H>
+__device__ __forceinline__ RowVec<H> fold_rows(const float* base, int n, int lane) {
+  RowVec<H> sum;
+  sum.zero();
+  int i = 0;
+  for (; i + 8 <= n; i += 8) {
+    RowVec<H> p[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) p[u].load_plain(base + (int64_t)(i + u) * H, lane);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) sum.add(p[u]);
+  }
+  for (; i < n; ++i) {
+    RowVec<H> p;
+    p.load_plain(base + (int64_t)i * H, lane);
+    sum.add(p);
+  }
+  return sum;
+}
+
 // Work items: [0, n_hsegs) heavy segments (long tasks first), then one item per row.
 template <int H>
-__global__ void __launch_bounds__(kSpmmThreads)
+__global__ void __launch_bounds__(kSpmmThreads, H <= 128 ? 3 : 2)
 k_spmm(kgb_csr_t g, EdgeW e, const float* __restrict__ x, int64_t ldx, float* __restrict__ y, int64_t ldy, float beta,
-       const float* __restrict__ bias, int relu, float* __restrict__ rowsum2, float* __restrict__ partial, float* __restrict__ partial2,
-       int32_t* __restrict__ ticket) {
+       const float* __restrict__ bias, int relu, float* __restrict__ rowsum2, HeavyBufs hb) {
+  float* __restrict__ partial = hb.partial;
+  float* __restrict__ partial2 = hb.partial2;
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   const int64_t n_items = (int64_t)g.n_hsegs + g.n_rows;
   for (int64_t item = warp0; item < n_items; item += n_warps) {
     if (item < g.n_hsegs) {
-      const int seg = (int)item;
+      const int seg = g.hseg_order ? __ldg(g.hseg_order + item) : (int)item;
       const int hr = __ldg(g.hseg_hrow + seg);
       const int row = __ldg(g.hrow_id + hr);
       const int seg0 = __ldg(g.hrow_segptr + hr), seg1 = __ldg(g.hrow_segptr + hr + 1);
@@ -125,25 +156,43 @@ k_spmm(kgb_csr_t g, EdgeW e, const float* __restrict__ x, int64_t ldx, float* __
         }
       }
       __threadfence();  // publish this partial before taking a ticket
+      // Two-level fold, each level done by the last finisher and always in index order (deterministic):
+      // KGB_FOLD consecutive segments -> one group partial; the row's group partials -> the output row.
+      const int P = seg1 - seg0;
+      const int gi = (seg - seg0) / KGB_FOLD;
+      const int gsz = min(KGB_FOLD, P - gi * KGB_FOLD);
+      const int grp0 = __ldg(g.hrow_grpptr + hr), ngrp = __ldg(g.hrow_grpptr + hr + 1) - grp0;
+      const int gid = grp0 + gi;
       int t = 0;
-      if (lane == 0) t = atomicAdd(ticket + hr, 1);
+      if (lane == 0) t = atomicAdd(hb.ticket1 + gid, 1);
       t = __shfl_sync(0xffffffffu, t, 0);
-      if (t == seg1 - seg0 - 1) {  // last segment of the row to finish: fold in segment order
-        __threadfence();
-        RowVec<H> sum;
-        sum.zero();
-        for (int s = seg0; s < seg1; ++s) {
-          RowVec<H> p;
-          p.load_plain(partial + (int64_t)s * H, lane);
-          sum.add(p);
+      if (t != gsz - 1) continue;
+      __threadfence();
+      {
+        RowVec<H> sum = fold_rows<H>(partial + (int64_t)(seg0 + gi * KGB_FOLD) * H, gsz, lane);
+        sum.store(hb.gpartial + (int64_t)gid * H, lane);
+        if (rowsum2 && lane < e.bins) {
+          float t2 = 0.f;
+          const float* p2 = partial2 + (int64_t)(seg0 + gi * KGB_FOLD) * e.bins + lane;
+          for (int s = 0; s < gsz; ++s) t2 += __ldcg(p2 + (int64_t)s * e.bins);
+          hb.gpartial2[(int64_t)gid * e.bins + lane] = t2;
         }
+        if (lane == 0) hb.ticket1[gid] = 0;  // leave the counters clean for the next launch
+      }
+      __threadfence();
+      if (lane == 0) t = atomicAdd(hb.ticket + hr, 1);
+      t = __shfl_sync(0xffffffffu, t, 0);
+      if (t != ngrp - 1) continue;
+      __threadfence();
+      {
+        RowVec<H> sum = fold_rows<H>(hb.gpartial + (int64_t)grp0 * H, ngrp, lane);
         write_row<H>(sum, y + (int64_t)row * ldy, beta, bias, relu, lane);
         if (rowsum2 && lane < e.bins) {
           float t2 = 0.f;
-          for (int s = seg0; s < seg1; ++s) t2 += __ldcg(partial2 + (int64_t)s * e.bins + lane);
+          for (int s = 0; s < ngrp; ++s) t2 += __ldcg(hb.gpartial2 + (int64_t)(grp0 + s) * e.bins + lane);
           rowsum2[(int64_t)row * e.bins + lane] = t2;
         }
-        if (lane == 0) ticket[hr] = 0;  // leave the counters clean for the next launch
+        if (lane == 0) hb.ticket[hr] = 0;
       }
     } else {
       const int row = (int)(item - g.n_hsegs);
@@ -188,9 +237,10 @@ int check_csr(const kgb_csr_t* g, const char* who) {
 
 using namespace kgb;
 
-extern "C" size_t kgb_spmm_scratch_bytes(int32_t n_hrows, int32_t n_hsegs, int32_t h) {
-  return align_up((size_t)n_hsegs * h * sizeof(float), 256) + align_up((size_t)n_hsegs * KGB_MAX_BINS * sizeof(float), 256) +
-         align_up((size_t)n_hrows * sizeof(int32_t), 256) + 256;
+extern "C" size_t kgb_spmm_scratch_bytes(int32_t n_hrows, int32_t n_hsegs, int32_t n_hgroups, int32_t h) {
+  return align_up((size_t)n_hrows * 4, 256) + align_up((size_t)n_hgroups * 4, 256) +
+         align_up((size_t)n_hsegs * KGB_MAX_BINS * 4, 256) + align_up((size_t)n_hgroups * KGB_MAX_BINS * 4, 256) +
+         align_up((size_t)n_hsegs * h * 4, 256) + align_up((size_t)n_hgroups * h * 4, 256) + 256;
 }
 
 extern "C" int kgb_spmm(const kgb_csr_t* csr, const float* ew, const int32_t* wperm, const float* ew2, float* rowsum2,
@@ -205,23 +255,25 @@ extern "C" int kgb_spmm(const kgb_csr_t* csr, const float* ew, const int32_t* wp
   KGB_REQUIRE((ew2 == nullptr) == (rowsum2 == nullptr), "spmm: ew2 and rowsum2 go together");
   KGB_REQUIRE(!ew2 || (rowsum2_bins >= 1 && rowsum2_bins <= KGB_MAX_BINS), "spmm: rowsum2_bins must be in [1, %d]", KGB_MAX_BINS);
   KGB_REQUIRE(!bias || aligned16(bias), "spmm: bias must be 16-byte aligned");
-  float* partial = nullptr;
-  float* partial2 = nullptr;
-  int32_t* ticket = nullptr;
+  HeavyBufs hb{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   if (csr->n_hsegs > 0) {
-    if (scratch_bytes < kgb_spmm_scratch_bytes(csr->n_hrows, csr->n_hsegs, h) || !scratch) {
-      set_error("spmm: scratch %zu < %zu", scratch_bytes, kgb_spmm_scratch_bytes(csr->n_hrows, csr->n_hsegs, h));
+    KGB_REQUIRE(csr->hrow_grpptr && csr->n_hgroups > 0, "spmm: hrow_grpptr / n_hgroups missing");
+    const size_t need = kgb_spmm_scratch_bytes(csr->n_hrows, csr->n_hsegs, csr->n_hgroups, h);
+    if (scratch_bytes < need || !scratch) {
+      set_error("spmm: scratch %zu < %zu", scratch_bytes, need);
       return KGB_ERR_WORKSPACE;
     }
     Carver ws(scratch);
-    ticket = ws.take<int32_t>(csr->n_hrows);  // counters first: caller zeroes them once
-    partial2 = ws.take<float>((size_t)csr->n_hsegs * KGB_MAX_BINS);
-    partial = ws.take<float>((size_t)csr->n_hsegs * h);
+    hb.ticket = ws.take<int32_t>(csr->n_hrows);  // counters first: caller zeroes them once
+    hb.ticket1 = ws.take<int32_t>(csr->n_hgroups);
+    hb.partial2 = ws.take<float>((size_t)csr->n_hsegs * KGB_MAX_BINS);
+    hb.gpartial2 = ws.take<float>((size_t)csr->n_hgroups * KGB_MAX_BINS);
+    hb.partial = ws.take<float>((size_t)csr->n_hsegs * h);
+    hb.gpartial = ws.take<float>((size_t)csr->n_hgroups * h);
   }
   const EdgeW e{ew, wperm, ew2, ew2 ? rowsum2_bins : 1};
   const unsigned grid = spmm_grid((int64_t)csr->n_hsegs + csr->n_rows);
-  KGB_DISPATCH_H(h, (k_spmm<H><<<grid, kSpmmThreads, 0, stream>>>(*csr, e, x, ldx, y, ldy, beta, bias, relu, rowsum2, partial, partial2,
-                                                               ticket)));
+  KGB_DISPATCH_H(h, (k_spmm<H><<<grid, kSpmmThreads, 0, stream>>>(*csr, e, x, ldx, y, ldy, beta, bias, relu, rowsum2, hb)));
   KGB_LAUNCH_OK();
   return KGB_OK;
 }

@@ -127,6 +127,7 @@ class HeteroGatLayerFn(torch.autograd.Function):
             for ji, job in enumerate(jobs):
                 lo, hi, R, S = job.rel_ids[0], job.rel_ids[-1] + 1, job.R, job.src_type
                 first, last = ji == 0, ji == len(jobs) - 1
+                job.schedule(h)
                 a_s, a_d = _f(job.n_src, R, dev), _f(n_t, R, dev)
                 _lib.rowdot(x[S], Vs[lo:hi], a_s, h, R, 0)
                 _lib.rowdot(x[T], Vd[lo:hi], a_d, h, R, 0)

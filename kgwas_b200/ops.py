@@ -54,28 +54,31 @@ class HeteroSageLayerFn(torch.autograd.Function):
             scale = meta.rel_scale[T]
             n_t = plan.num_nodes[T]
             out = _empty(n_t, h, Wl)
-            first = True
-            for job in plan.jobs[T]:
-                lo, hi = job.rel_ids[0], job.rel_ids[-1] + 1
-                R, xs_ = job.R, x[job.src_type]
-                if job.mode == "xf":
-                    wcat = Wl[lo:hi].reshape(R * h, h)                       # view: rows k*h.. = W_l^k
-                    z = _empty(job.n_src, R * h, Wl)
-                    _lib.gemm(KGB_NT, xs_, wcat, z, job.n_src, R * h, h, alpha=scale)
-                    _lib.spmm(job.csr, z.view(job.n_src * R, h), out, h, ew=job.w_mean, beta=0.0 if first else 1.0)
-                else:
-                    A = _empty(n_t, R * h, Wl)
-                    _lib.spmm(job.csr, xs_, A.view(n_t * R, h), h, ew=job.w_mean)
-                    wcat_t = Wl[lo:hi].permute(1, 0, 2).reshape(h, R * h)    # [h, R*h]: out += A . wcat_t^T
-                    _lib.gemm(KGB_NT, A, wcat_t, out, n_t, h, R * h, alpha=scale, beta=0.0 if first else 1.0)
-                    saved_A[(T, job.src_type)] = A
-                first = False
+            # root term first (dense, overwrites), then every job accumulates; the last writer applies the ReLU.
+            # (A gather-reduce that accumulates re-reads one row per warp, which hides latency far better than
+            # a GEMM epilogue re-reading C.)
             w_root = Wr[a:b].sum(0)
             bias = bl[a:b].sum(0)
             if scale != 1.0:
                 bias = bias * scale
-            _lib.gemm(KGB_NT, x[T], w_root, out, n_t, h, h, alpha=scale, beta=0.0 if first else 1.0, bias=bias,
-                      relu=meta.relu)
+            jobs = plan.jobs[T]
+            _lib.gemm(KGB_NT, x[T], w_root, out, n_t, h, h, alpha=scale, bias=bias, relu=meta.relu and not jobs)
+            for ji, job in enumerate(jobs):
+                lo, hi = job.rel_ids[0], job.rel_ids[-1] + 1
+                R, xs_ = job.R, x[job.src_type]
+                job.schedule(h)
+                last_relu = meta.relu and ji == len(jobs) - 1
+                if job.mode == "xf":
+                    wcat = Wl[lo:hi].reshape(R * h, h)                       # view: rows k*h.. = W_l^k
+                    z = _empty(job.n_src, R * h, Wl)
+                    _lib.gemm(KGB_NT, xs_, wcat, z, job.n_src, R * h, h, alpha=scale)
+                    _lib.spmm(job.csr, z.view(job.n_src * R, h), out, h, ew=job.w_mean, beta=1.0, relu=last_relu)
+                else:
+                    A = _empty(n_t, R * h, Wl)
+                    _lib.spmm(job.csr, xs_, A.view(n_t * R, h), h, ew=job.w_mean)
+                    wcat_t = Wl[lo:hi].permute(1, 0, 2).reshape(h, R * h)    # [h, R*h]: out += A . wcat_t^T
+                    _lib.gemm(KGB_NT, A, wcat_t, out, n_t, h, R * h, alpha=scale, beta=1.0, relu=last_relu)
+                    saved_A[(T, ji)] = A
             outs.append(out)
         ctx.meta = meta
         ctx.saved_A = saved_A
@@ -108,7 +111,9 @@ class HeteroSageLayerFn(torch.autograd.Function):
                 return dx[t], 0.0
             return dx[t], 1.0
 
-        for T, d_out in zip(plan.dst_types, d_outs):
+        # largest destination type first: its dense d x = g . W_root then is the first (overwriting) writer
+        order = sorted(range(len(plan.dst_types)), key=lambda i: -plan.num_nodes[plan.dst_types[i]])
+        for T, d_out in [(plan.dst_types[i], d_outs[i]) for i in order]:
             if d_out is None:
                 continue
             a, b = plan.rel_range[T]
@@ -129,7 +134,7 @@ class HeteroSageLayerFn(torch.autograd.Function):
             if need_x[T]:
                 buf, beta = dx_target(T)
                 _lib.gemm(KGB_NN, g, Wr[a:b].sum(0), buf, n_t, h, h, beta=beta)
-            for job in plan.jobs[T]:
+            for ji, job in enumerate(plan.jobs[T]):
                 lo, hi = job.rel_ids[0], job.rel_ids[-1] + 1
                 R, S = job.R, job.src_type
                 if job.mode == "xf":
@@ -141,7 +146,7 @@ class HeteroSageLayerFn(torch.autograd.Function):
                         buf, beta = dx_target(S)
                         _lib.gemm(KGB_NN, dz, Wl[lo:hi].reshape(R * h, h), buf, job.n_src, h, R * h, beta=beta)
                 else:
-                    A = ctx.saved_A[(T, S)]
+                    A = ctx.saved_A[(T, ji)]
                     if need_w:
                         dwt = _empty(h, R * h, g)                              # [h_out, R*h_in]
                         _lib.gemm(KGB_TN, g, A, dwt, h, R * h, n_t)

@@ -48,9 +48,12 @@ class PairJob:
         group = dst * R + slot                                   # softmax / mean group of every edge
         if self.mode == "xf":
             job_src, job_dst, n_js, n_jd = src * R + slot, dst, n_src * R, n_dst
+            presort = slot * n_src + src       # slots of a row ordered by (relation slot, source): groups stay contiguous
         else:
             job_src, job_dst, n_js, n_jd = src, group, n_src, n_dst * R
-        self.csr, self.eperm, self.tcsr, self.t_eperm = _lib.csr_build(job_src, job_dst, n_js, n_jd)
+            presort = None                     # ordered by source: heavy rows sweep the gathered table front to back
+        self.csr, self.eperm, self.tcsr, self.t_eperm = _lib.csr_build(job_src, job_dst, n_js, n_jd, sort_cols=True,
+                                                                        presort_key=presort)
         # group bookkeeping (exact integer work; plan time only)
         deg = torch.bincount(group, minlength=n_dst * R)
         self.group_deg = deg.to(torch.int32)
@@ -64,6 +67,15 @@ class PairJob:
         else:
             self.group_rowptr = self.csr.rowptr
         self._gcsr = None
+        self._scheduled_h = None
+
+    def schedule(self, h: int):
+        """L2-window scheduling of the heavy segments for feature width h (idempotent)."""
+        if self._scheduled_h != h:
+            self.csr.schedule_for_l2(4 * h)
+            self.tcsr.schedule_for_l2(4 * h)
+            self._scheduled_h = h
+        return self
 
     @property
     def gcsr(self) -> "_lib.Csr":

@@ -16,11 +16,15 @@ from typing import Dict, List, Tuple
 import numpy as np
 
 
-def csr_from_coo_ref(src: np.ndarray, dst: np.ndarray, n_src: int, n_dst: int):
+def csr_from_coo_ref(src: np.ndarray, dst: np.ndarray, n_src: int, n_dst: int, sort_cols: bool = False):
     """Returns rowptr, col, eperm, t_rowptr, t_col, t_eperm (see include/kgwas_b200.h)."""
     src = np.asarray(src, dtype=np.int64)
     dst = np.asarray(dst, dtype=np.int64)
-    eperm = np.argsort(dst, kind="stable")
+    if sort_cols:      # slots of a row ordered by (source, original edge id)
+        by_src = np.argsort(src, kind="stable")
+        eperm = by_src[np.argsort(dst[by_src], kind="stable")]
+    else:
+        eperm = np.argsort(dst, kind="stable")
     col = src[eperm]
     rowptr = np.zeros(n_dst + 1, dtype=np.int64)
     np.add.at(rowptr, dst + 1, 1)

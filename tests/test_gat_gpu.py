@@ -107,6 +107,10 @@ def test_hetero_gat_forward_backward(cuda, h, scale, aggr):
     assert _rel_err(out_g, out_r) < RTOL
     p_ref, p_64, p_g = dict(ref.named_parameters()), dict(ref64.named_parameters()), dict(ours.named_parameters())
     assert p_ref.keys() == p_g.keys()
+    # att_dst / lin_dst only act through the softmax shift: their true gradient is ~0 whenever the groups
+    # have one edge or same-sign logits, so errors are judged against the layer-wide gradient scale
+    floor = 1e-5 * max(p.grad.abs().max().item() for p in p_64.values()
+                       if not isinstance(p, torch.nn.parameter.UninitializedParameter) and p.grad is not None)
     for k in p_ref:
         lazy = isinstance(p_ref[k], torch.nn.parameter.UninitializedParameter)
         assert lazy == isinstance(p_g[k], torch.nn.parameter.UninitializedParameter), k
@@ -116,10 +120,8 @@ def test_hetero_gat_forward_backward(cuda, h, scale, aggr):
             assert p_g[k].grad is None, k
             continue
         assert p_g[k].grad is not None, k
-        if p_64[k].grad.abs().max().item() == 0:
-            continue
-        err = _rel_err(p_g[k].grad, p_64[k].grad)
-        assert err < 2e-3, (k, err, _rel_err(p_ref[k].grad, p_64[k].grad))
+        diff = (p_g[k].grad.double().cpu() - p_64[k].grad).abs().max().item()
+        assert diff <= 2e-3 * p_64[k].grad.abs().max().item() + floor, (k, diff, p_64[k].grad.abs().max().item())
 
 
 def test_gat_microcases(cuda):

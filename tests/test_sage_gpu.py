@@ -57,6 +57,7 @@ def test_hetero_sage_forward_backward(cuda, h, scale, aggr):
     p_ref, p_64, p_g = dict(ref.named_parameters()), dict(ref64.named_parameters()), dict(ours.named_parameters())
     assert p_ref.keys() == p_g.keys()
     worst = 0.0
+    floor = 1e-5 * max(p.grad.abs().max().item() for p in p_64.values() if p.grad is not None)
     for k in p_ref:
         if p_ref[k].grad is None:
             assert p_g[k].grad is None, f"{k}: reference leaves grad None (unused relation), ours does not"
@@ -66,10 +67,8 @@ def test_hetero_sage_forward_backward(cuda, h, scale, aggr):
         if scale_ == 0:
             assert p_g[k].grad.abs().max().item() == 0
             continue
-        err = _rel_err(p_g[k].grad, p_64[k].grad)
-        worst = max(worst, err)
-        assert err < 1e-3, (k, err, _rel_err(p_ref[k].grad, p_64[k].grad))
-    assert worst < 1e-3
+        diff = (p_g[k].grad.double().cpu() - p_64[k].grad).abs().max().item()
+        assert diff <= 1e-3 * scale_ + floor, (k, diff, scale_)
 
 
 def test_sage_microcases(cuda):
