@@ -1,0 +1,148 @@
+"""``KGWAS`` with the reference's surface (kgwas/kgwas.py:25-272): ``initialize_model`` / ``train`` /
+``load_pretrained`` keep their signatures and defaults; the model is the CUDA-backed drop-in HeteroGNN,
+mini-batches come from the PyG-free full-neighbour loader."""
+from __future__ import annotations
+
+import os
+import pickle
+from copy import deepcopy
+
+import numpy as np
+import pandas as pd
+import torch
+import torch.nn.functional as F
+import torch.optim as optim
+from tqdm import tqdm
+
+from .loader import NeighborLoader
+from .model import HeteroGNN
+from .postprocess import compute_metrics, find_closest_x, storey_ribshirani_integrate
+from .utils import evaluate_minibatch_clean, load_pretrained, print_sys, save_model
+
+
+class KGWAS:
+    _model_cls = HeteroGNN          # tests substitute the CPU oracle here to exercise the host logic without a GPU
+
+    def __init__(self, data, weight_bias_track=False, device="cuda", proj_name="KGWAS", exp_name="KGWAS", seed=42):
+        torch.manual_seed(seed)
+        torch.cuda.manual_seed(seed)
+        np.random.seed(seed)
+        self.seed = seed
+        torch.backends.cudnn.enabled = False                       # kgwas.py:37
+        self.device = device if torch.cuda.is_available() else "cpu"
+        self.data, self.data_path = data, data.data_path
+        self.wandb = False
+        if weight_bias_track:
+            import wandb
+            wandb.init(project=proj_name, name=exp_name)
+            self.wandb = wandb
+        self.exp_name = exp_name
+
+    def initialize_model(self, gnn_num_layers=2, gnn_hidden_dim=128, gnn_backbone="GAT", gnn_aggr="sum",
+                         gat_num_head=1, no_relu=False):
+        self.config = {"gnn_num_layers": gnn_num_layers, "gnn_hidden_dim": gnn_hidden_dim,
+                       "gnn_backbone": gnn_backbone, "gnn_aggr": gnn_aggr, "gat_num_head": gat_num_head}
+        self.gnn_num_layers = gnn_num_layers
+        self.model = self._model_cls(self.data.data, gnn_hidden_dim, 1, gnn_num_layers, gnn_backbone, gnn_aggr,
+                                     self.data.snp_init_dim_size, self.data.gene_init_dim_size,
+                                     self.data.go_init_dim_size, gat_num_head, no_relu=no_relu).to(self.device)
+
+    def load_pretrained(self, path):
+        with open(os.path.join(path, "config.pkl"), "rb") as f:
+            config = pickle.load(f)
+        self.initialize_model(**config)
+        self.config = config
+        self.model = load_pretrained(path, self.model)
+        self.best_model = self.model
+        self.kgwas_res = pd.read_csv(os.path.join(path, "pred.csv"), sep=None, engine="python")
+        self.save_name = path.split("/")[-1]
+
+    def _ld_weights(self, n_id):
+        """Per-seed LDSC weights (float64, as in kgwas.py:142-143) through one vectorised lookup table
+        instead of a Python dict lookup per SNP per step."""
+        if getattr(self, "_w_table", None) is None:
+            table = np.ones(len(self.data.idx2id["SNP"]), dtype=np.float64)
+            ids = np.array([self.data.id2idx["SNP"][r] for r in self.data.rs_id_to_ldsc_weight], dtype=np.int64)
+            table[ids] = np.fromiter(self.data.rs_id_to_ldsc_weight.values(), dtype=np.float64, count=len(ids))
+            self._w_table = torch.from_numpy(table)
+        return self._w_table[n_id.cpu()].to(self.device)
+
+    def train(self, batch_size=512, num_workers=0, lr=1e-4, weight_decay=5e-4, epoch=10, save_best_model=True,
+              save_name=None, data_to_cuda=False):
+        total_epoch = epoch
+        save_name = self.exp_name if save_name is None else save_name
+        self.save_name = save_name
+        print_sys("Creating data loader...")
+        kwargs = {"batch_size": batch_size, "num_workers": num_workers, "drop_last": True}
+        eval_kwargs = {"batch_size": 512, "num_workers": num_workers, "drop_last": False}
+        if data_to_cuda:
+            self.data.data = self.data.data.to(self.device)
+        hops = [-1] * self.gnn_num_layers
+        self.train_loader = NeighborLoader(self.data.data, num_neighbors=hops, sampler=None,
+                                           input_nodes=self.data.train_input_nodes, **kwargs)
+        self.val_loader = NeighborLoader(self.data.data, num_neighbors=hops, input_nodes=self.data.val_input_nodes, **kwargs)
+        self.test_loader = NeighborLoader(self.data.data, num_neighbors=hops, input_nodes=self.data.test_input_nodes,
+                                          **eval_kwargs)
+        infer_idx = np.array([self.data.id2idx["SNP"][i] for i in self.data.lr_uni.ID.values])
+        self.infer_loader = NeighborLoader(self.data.data, num_neighbors=hops, input_nodes=("SNP", infer_idx),
+                                           **eval_kwargs)
+        optimizer = optim.Adam(self.model.parameters(), lr=lr, weight_decay=weight_decay)   # before the first forward
+        loss_fct, min_val = F.mse_loss, -1000
+        self.best_model = deepcopy(self.model).to(self.device)
+        print_sys("Start Training...")
+        for ep in range(total_epoch):
+            self.model.train()
+            for step, batch in enumerate(tqdm(self.train_loader, desc=f"Training Progress Epoch {ep + 1}/{total_epoch}",
+                                              total=len(self.train_loader))):
+                optimizer.zero_grad()
+                batch = batch.to(self.device)
+                bs = batch["SNP"].batch_size
+                pred = self.model(batch.x_dict, batch.edge_index_dict, bs).reshape(-1)
+                y_batch = batch["SNP"].y[:bs]
+                ld_weight = self._ld_weights(batch["SNP"]["n_id"][:bs])
+                loss = torch.mean(ld_weight * (pred - y_batch) ** 2)                     # kgwas.py:145
+                if self.wandb:
+                    self.wandb.log({"training_loss": loss.item()})
+                loss.backward()
+                optimizer.step()
+                if step % 500 == 0 and step >= 500:
+                    print_sys("Epoch {} Step {} Train Loss: {:.4f}".format(ep + 1, step + 1, loss.item()))
+            val_res = evaluate_minibatch_clean(self.val_loader, self.model, self.device)
+            val_metrics = compute_metrics(val_res, False, -1, -1, loss_fct)
+            print_sys("Epoch {}: Validation MSE: {:.4f} Validation Pearson: {:.4f}. ".format(
+                ep + 1, val_metrics["mse"], val_metrics["pearsonr"]))
+            if self.wandb:
+                for k, v in val_metrics.items():
+                    self.wandb.log({"val_" + k: v})
+            if val_metrics["pearsonr"] > min_val:                                      # keep the best by val Pearson
+                min_val = val_metrics["pearsonr"]
+                self.best_model = deepcopy(self.model)
+        if save_best_model:
+            save_model_path = self.data_path + "/model/"
+            print_sys("Saving models to " + os.path.join(save_model_path, save_name))
+            save_model(self.best_model, self.config, os.path.join(save_model_path, save_name))
+        test_res = evaluate_minibatch_clean(self.test_loader, self.best_model, self.device)
+        self.test_metric = compute_metrics(test_res, False, -1, -1, loss_fct)
+        if self.wandb:
+            for k, v in self.test_metric.items():
+                self.wandb.log({"test_" + k: v})
+        infer_res = evaluate_minibatch_clean(self.infer_loader, self.best_model, self.device)
+        self._postprocess(infer_res["pred"], save_name, save_best_model)
+
+    def _postprocess(self, pred, save_name, save_best_model):
+        """Storey-Tibshirani re-weighting + calibration + CSV output (kgwas.py:191-212)."""
+        self.data.lr_uni["pred"] = pred
+        lr_uni_to_save = deepcopy(self.data.lr_uni)
+        self.data.lr_uni["abs_pred"] = np.abs(self.data.lr_uni["pred"])
+        self.data.lr_uni["SR_P_val"] = storey_ribshirani_integrate(self.data.lr_uni, column="abs_pred", num_bins=500)
+        self.data.lr_uni["SR"] = -np.log10(self.data.lr_uni["SR_P_val"].astype(float).values)
+        lr_uni_to_save["P_weighted"] = self.data.lr_uni["SR_P_val"]
+        scale_factor = find_closest_x(lr_uni_to_save)
+        lr_uni_to_save["KGWAS_P"] = (scale_factor * lr_uni_to_save["P_weighted"]).clip(lower=0, upper=1)
+        out_dir = self.data_path + "/model_pred/new_experiments/"
+        os.makedirs(out_dir, exist_ok=True)
+        lr_uni_to_save.to_csv(out_dir + save_name + "_pred.csv", index=False, sep="\t")
+        print("KGWAS prediction and p-values saved to " + out_dir + save_name + "_pred.csv")
+        if save_best_model:
+            lr_uni_to_save.to_csv(self.data_path + "/model/" + save_name + "/pred.csv", index=False, sep="\t")
+        self.kgwas_res = lr_uni_to_save
