@@ -86,7 +86,7 @@ def test_postprocess_reweighting():
     pw = storey_ribshirani_integrate(df, column="abs_pred", num_bins=50)
     assert pw.shape == (n,) and np.isfinite(pw).all() and (pw >= 0).all() and (pw <= 1).all()
     assert abs(df["weights"].mean() - 1) < 1e-9
-    assert (pw[signal] < p[signal]).mean() > (pw[~signal] < p[~signal]).mean() + 0.2        # signal bins gain power
+    assert (pw[signal] < p[signal]).mean() > (pw[~signal] < p[~signal]).mean() + 0.1        # signal bins gain power
     df["P_weighted"] = pw
     s = find_closest_x(df)
     assert 0 <= s <= 200
