@@ -232,7 +232,7 @@ def ours(args):
         dist.init_process_group("nccl", device_id=dev)
     if world > 1:
         from kgwas_b200 import dist as kdist
-        return kdist.bench_sharded(args, rank, world, dev)
+        return kdist.bench_sharded(args, rank, world, dev, {"ClockSampler": ClockSampler, "workload_config": workload_config})
 
     h, L = args.hidden, args.layers
     data, y, w = make_problem(args, args.scale, dev)

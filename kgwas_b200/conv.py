@@ -169,11 +169,15 @@ class SAGEConv(nn.Module):
         return f"SAGEConv({self.in_channels}, {self.out_channels}, aggr=mean)"
 
 
-def _hetero_sage(convs: Dict[EdgeType, SAGEConv], x_dict, edge_index_dict, aggr: str, relu: bool):
-    """Fused multi-relation SAGE layer (all widths equal)."""
+def _hetero_sage(convs: Dict[EdgeType, SAGEConv], x_dict, edge_index_dict, aggr: str, relu: bool, shard=None):
+    """Fused multi-relation SAGE layer (all widths equal).  ``shard``: a dist.ShardContext for SNP-sharded runs."""
     node_types = list(x_dict.keys())
     num_nodes = {t: int(x.size(0)) for t, x in x_dict.items()}
-    plan = get_plan(edge_index_dict, num_nodes, frozenset(convs.keys()))
+    if shard is not None:
+        with shard.building_plan():
+            plan = get_plan(edge_index_dict, num_nodes, frozenset(convs.keys()))
+    else:
+        plan = get_plan(edge_index_dict, num_nodes, frozenset(convs.keys()))
     if not plan.rel_order:
         return {}
     h = convs[plan.rel_order[0]].out_channels
@@ -187,13 +191,16 @@ def _hetero_sage(convs: Dict[EdgeType, SAGEConv], x_dict, edge_index_dict, aggr:
     for T in plan.dst_types:
         a, b = plan.rel_range[T]
         rel_scale[T] = 1.0 if aggr == "sum" else 1.0 / (b - a)
-    meta = _SageLayerCtx(plan, node_types, h, relu, rel_scale)
+    meta = _SageLayerCtx(plan, node_types, h, relu, rel_scale, shard.root_range if shard is not None else None)
     cs = [convs[et] for et in plan.rel_order]
     for c, et in zip(cs, plan.rel_order):
         c.materialize(h, h)
     outs = HeteroSageLayerFn.apply(meta, *[x_dict[t] for t in node_types], *[c.lin_l.weight for c in cs],
                                    *[c.lin_l.bias for c in cs], *[c.lin_r.weight for c in cs])
-    return dict(zip(plan.dst_types, outs))
+    out = dict(zip(plan.dst_types, outs))
+    if shard is not None:
+        out = shard.combine(out, relu)     # sum the partial rows of shared node types across ranks, then ReLU
+    return out
 
 
 # -------------------------------------------------------------------------------------------------
@@ -218,6 +225,7 @@ class HeteroConv(nn.Module):
         self.convs = nn.ModuleDict({_key(k): v for k, v in convs.items()})
         self._edge_types: List[EdgeType] = list(convs.keys())
         self.aggr = aggr
+        self.shard = None                 # dist.ShardContext when the SNP axis is sharded over several GPUs
         self._register_load_state_dict_pre_hook(self._rename_pyg24_keys)
 
     def _rename_pyg24_keys(self, state_dict, prefix, *args):
@@ -237,7 +245,10 @@ class HeteroConv(nn.Module):
         widths = {int(x.size(-1)) for x in x_dict.values()}
         fusable = self.aggr in ("sum", "mean") and len(widths) == 1 and not kwargs_dict
         if fusable and kinds == {SAGEConv}:
-            return _hetero_sage(convs, x_dict, edge_index_dict, self.aggr, _fuse_relu)
+            return _hetero_sage(convs, x_dict, edge_index_dict, self.aggr, _fuse_relu, self.shard)
+        if self.shard is not None:
+            raise NotImplementedError("SNP-sharded multi-GPU execution is implemented for the hetero-SAGE layer "
+                                      "(BASELINE config 4); GAT needs cross-rank softmax statistics (DESIGN.md)")
         from .gat import GATConv, hetero_gat   # noqa: local import keeps module load light
         if self.aggr in ("sum", "mean") and len(widths) == 1 and kinds == {GATConv}:
             return hetero_gat(convs, x_dict, edge_index_dict, self.aggr, _fuse_relu, kwargs_dict)

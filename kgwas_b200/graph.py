@@ -228,17 +228,19 @@ def _zipf_sampler(rng: np.random.Generator, n: int, alpha: float):
     cdf = np.cumsum(p / p.sum())
     perm = rng.permutation(n)
 
-    def draw(size):
-        r = np.searchsorted(cdf, rng.random(size), side="left")
+    def draw(size, rng_=None):
+        r = np.searchsorted(cdf, (rng_ or rng).random(size), side="left")
         return perm[np.minimum(r, n - 1)]
 
     return draw
 
 
-def make_synth_edges(scale: float = 1.0, seed: int = 42, node_scale: float | None = None):
+def make_synth_edges(scale: float = 1.0, seed: int = 42, node_scale: float | None = None, snp_block: int = 0):
     """Raw (pre-transform) ``edge_index_all`` dict + node counts of kgwas-synth-v1.
-    ``scale`` shrinks edge counts, ``node_scale`` (default = scale) shrinks node counts."""
+    ``scale`` shrinks edge counts, ``node_scale`` (default = scale) shrinks node counts.  ``snp_block`` > 0 draws a
+    different block of SNP nodes (and SNP->Gene edges) against the SAME gene / GO graph: block b of a multi-GPU run."""
     rng = np.random.default_rng(seed)
+    rng_snp = rng if snp_block == 0 else np.random.default_rng(seed + 7919 * snp_block)
     node_scale = scale if node_scale is None else node_scale
     nodes = {k: max(8, int(round(v * node_scale))) for k, v in SYNTH_NODES.items()}
     gene_draw = _zipf_sampler(rng, nodes["Gene"], 1.1)
@@ -248,8 +250,8 @@ def make_synth_edges(scale: float = 1.0, seed: int = 42, node_scale: float | Non
     for (s, rel, t), e_raw in SYNTH_RELATIONS:
         e = max(1, int(round(e_raw * scale)))
         if s == "SNP":
-            src = rng.integers(0, nodes["SNP"], size=e)          # uniform => Poisson degrees, many isolated SNPs
-            dst = gene_draw(e)
+            src = rng_snp.integers(0, nodes["SNP"], size=e)      # uniform => Poisson degrees, many isolated SNPs
+            dst = gene_draw(e) if snp_block == 0 else gene_draw(e, rng_snp)
         elif t == "Gene":
             src, dst = gene_draw(e), gene_draw(e)
         else:
@@ -259,13 +261,14 @@ def make_synth_edges(scale: float = 1.0, seed: int = 42, node_scale: float | Non
 
 
 def make_synth_kg(scale: float = 1.0, seed: int = 42, hidden: int | None = None, node_scale: float | None = None,
-                  feature_dims: Dict[str, int] | None = None) -> HeteroData:
+                  feature_dims: Dict[str, int] | None = None, snp_block: int = 0) -> HeteroData:
     """kgwas-synth-v1 as a transformed ``HeteroData`` (27 edge types at any scale).
 
     ``hidden`` given: every node type gets ``[N, hidden]`` N(0,1) features (the conv path starts after
     the input MLPs).  Otherwise fast-mode raw widths (SNP 20, Gene 5120, GO 128) or ``feature_dims``."""
-    edges, nodes = make_synth_edges(scale, seed, node_scale)
+    edges, nodes = make_synth_edges(scale, seed, node_scale, snp_block)
     g = torch.Generator().manual_seed(seed)
+    g_snp = g if snp_block == 0 else torch.Generator().manual_seed(seed + 7919 * snp_block)
     data = HeteroData()
     dims = {"SNP": 20, "Gene": 5120, "CellularComponent": 128, "BiologicalProcess": 128, "MolecularFunction": 128}
     if feature_dims:
@@ -275,7 +278,7 @@ def make_synth_kg(scale: float = 1.0, seed: int = 42, hidden: int | None = None,
         if hidden is None and t in ("CellularComponent", "BiologicalProcess", "MolecularFunction"):
             data[t].x = torch.rand((nodes[t], d), generator=g)     # kgwas_data.py:190
         else:
-            data[t].x = torch.randn((nodes[t], d), generator=g)
+            data[t].x = torch.randn((nodes[t], d), generator=g_snp if t == "SNP" else g)
     for k, ei in edges.items():
         data[k].edge_index = torch.from_numpy(ei)
     data = ToUndirected()(data)

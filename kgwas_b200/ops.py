@@ -24,8 +24,16 @@ def _empty(rows, cols, like):
 class _SageLayerCtx:
     """Static description handed to the autograd Function (not a tensor)."""
 
-    def __init__(self, plan: LayerPlan, node_types: List[str], h: int, relu: bool, rel_scale: Dict[str, float]):
+    def __init__(self, plan: LayerPlan, node_types: List[str], h: int, relu: bool, rel_scale: Dict[str, float],
+                 root_range: Optional[Dict[str, tuple]] = None):
         self.plan, self.node_types, self.h, self.relu, self.rel_scale = plan, node_types, h, relu, rel_scale
+        # SNP-sharded execution (dist.py): for a destination type whose rows are shared by all ranks, this rank
+        # adds the root term (and bias) only for rows [lo, hi); the partial outputs are summed across ranks and
+        # the ReLU runs after that sum, outside this Function.
+        self.root_range = root_range or {}
+
+    def fused_relu(self, T: str) -> bool:
+        return self.relu and T not in self.root_range
 
 
 class HeteroSageLayerFn(torch.autograd.Function):
@@ -62,12 +70,18 @@ class HeteroSageLayerFn(torch.autograd.Function):
             if scale != 1.0:
                 bias = bias * scale
             jobs = plan.jobs[T]
-            _lib.gemm(KGB_NT, x[T], w_root, out, n_t, h, h, alpha=scale, bias=bias, relu=meta.relu and not jobs)
+            relu_T = meta.fused_relu(T)
+            if T in meta.root_range:
+                r0, r1 = meta.root_range[T]
+                out.zero_()
+                _lib.gemm(KGB_NT, x[T][r0:r1], w_root, out[r0:r1], r1 - r0, h, h, alpha=scale, bias=bias)
+            else:
+                _lib.gemm(KGB_NT, x[T], w_root, out, n_t, h, h, alpha=scale, bias=bias, relu=relu_T and not jobs)
             for ji, job in enumerate(jobs):
                 lo, hi = job.rel_ids[0], job.rel_ids[-1] + 1
                 R, xs_ = job.R, x[job.src_type]
                 job.schedule(h)
-                last_relu = meta.relu and ji == len(jobs) - 1
+                last_relu = relu_T and ji == len(jobs) - 1
                 if job.mode == "xf":
                     wcat = Wl[lo:hi].reshape(R * h, h)                       # view: rows k*h.. = W_l^k
                     z = _empty(job.n_src, R * h, Wl)
@@ -119,21 +133,25 @@ class HeteroSageLayerFn(torch.autograd.Function):
             a, b = plan.rel_range[T]
             scale = meta.rel_scale[T]
             n_t = plan.num_nodes[T]
-            g = _lib.relu_bwd(d_out, outs[T]) if meta.relu else d_out.contiguous()
+            g = _lib.relu_bwd(d_out, outs[T]) if meta.fused_relu(T) else d_out.contiguous()
             if scale != 1.0:
                 g = g * scale
             for i in range(a, b):
                 used[i] = True
+            r0, r1 = meta.root_range.get(T, (0, n_t))          # rows whose root term this rank owns
             if need_w:
                 db = torch.empty(h, dtype=torch.float32, device=g.device)
-                _lib.wcolsum(g, h, db)
+                _lib.wcolsum(g[r0:r1], h, db)
                 dbl[a:b] = db
                 dwr = _empty(h, h, g)
-                _lib.gemm(KGB_TN, g, x[T], dwr, h, h, n_t)
+                _lib.gemm(KGB_TN, g[r0:r1], x[T][r0:r1], dwr, h, h, r1 - r0)
                 dWr[a:b] = dwr
             if need_x[T]:
                 buf, beta = dx_target(T)
-                _lib.gemm(KGB_NN, g, Wr[a:b].sum(0), buf, n_t, h, h, beta=beta)
+                if (r0, r1) != (0, n_t) and beta == 0.0:
+                    buf.zero_()
+                    beta = 1.0
+                _lib.gemm(KGB_NN, g[r0:r1], Wr[a:b].sum(0), buf[r0:r1], r1 - r0, h, h, beta=beta)
             for ji, job in enumerate(plan.jobs[T]):
                 lo, hi = job.rel_ids[0], job.rel_ids[-1] + 1
                 R, S = job.R, job.src_type

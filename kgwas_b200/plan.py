@@ -27,6 +27,7 @@ from . import _lib
 
 EdgeType = Tuple[str, str, str]
 MAX_SLOTS = 8      # KGB_MAX_BINS of the C ABI
+DEG_REDUCE = None  # set by kgwas_b200.dist while a sharded plan is built (all-reduce of the group degrees)
 
 
 class PairJob:
@@ -56,13 +57,16 @@ class PairJob:
                                                                         presort_key=presort)
         # group bookkeeping (exact integer work; plan time only)
         deg = torch.bincount(group, minlength=n_dst * R)
+        if DEG_REDUCE is not None:      # SNP-sharded graphs: in-degrees of shared destination nodes are global
+            deg = DEG_REDUCE(deg)
         self.group_deg = deg.to(torch.int32)
         w = (1.0 / deg.clamp(min=1).to(torch.float32))[group]    # SAGE mean: 1 / max(in-degree, 1)
+        local_deg = torch.bincount(group, minlength=n_dst * R) if DEG_REDUCE is not None else deg
         self.w_mean = w[self.eperm.long()].contiguous()          # CSR slot order
         if self.mode == "xf":
             # slots are (t, k)-sorted; group row pointers over the same slot order
             gp = torch.zeros(n_dst * R + 1, dtype=torch.int64, device=dev)
-            torch.cumsum(deg, 0, out=gp[1:])
+            torch.cumsum(local_deg, 0, out=gp[1:])
             self.group_rowptr = gp.to(torch.int32)
         else:
             self.group_rowptr = self.csr.rowptr
