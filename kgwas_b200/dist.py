@@ -64,7 +64,9 @@ class ShardContext:
 
     @contextlib.contextmanager
     def building_plan(self):
-        def reduce_deg(deg):
+        def reduce_deg(deg, dst_type):
+            if dst_type == SHARDED_TYPE:       # owned rows: every in-edge of a local SNP is local
+                return deg
             deg = deg.clone()
             dist.all_reduce(deg, op=dist.ReduceOp.SUM)
             return deg

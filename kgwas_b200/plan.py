@@ -58,7 +58,7 @@ class PairJob:
         # group bookkeeping (exact integer work; plan time only)
         deg = torch.bincount(group, minlength=n_dst * R)
         if DEG_REDUCE is not None:      # SNP-sharded graphs: in-degrees of shared destination nodes are global
-            deg = DEG_REDUCE(deg)
+            deg = DEG_REDUCE(deg, dst_type)
         self.group_deg = deg.to(torch.int32)
         w = (1.0 / deg.clamp(min=1).to(torch.float32))[group]    # SAGE mean: 1 / max(in-degree, 1)
         local_deg = torch.bincount(group, minlength=n_dst * R) if DEG_REDUCE is not None else deg

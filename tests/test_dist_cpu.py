@@ -48,7 +48,9 @@ def _worker(rank, world, port, ret):
         et = ("SNP", "TSS", "Gene")
         with shard.building_plan():
             from kgwas_b200 import plan
-            deg = plan.DEG_REDUCE(torch.bincount(local[et].edge_index[1], minlength=data["Gene"].num_nodes))
+            deg = plan.DEG_REDUCE(torch.bincount(local[et].edge_index[1], minlength=data["Gene"].num_nodes), "Gene")
+            own = torch.arange(3 + rank)
+            ok &= plan.DEG_REDUCE(own, "SNP") is own          # owned (sharded) rows: no collective, sizes may differ
         ok &= torch.equal(deg, torch.bincount(data[et].edge_index[1], minlength=data["Gene"].num_nodes))
         ok &= plan.DEG_REDUCE is None
         # 4. flat gradient all-reduce

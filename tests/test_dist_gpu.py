@@ -61,6 +61,7 @@ def _worker(rank, world, port, ret):
         dist.destroy_process_group()
 
 
+@pytest.mark.timeout(200)
 def test_two_gpu_sharded_matches_single(cuda):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
@@ -72,7 +73,10 @@ def test_two_gpu_sharded_matches_single(cuda):
     for p in procs:
         p.start()
     for p in procs:
-        p.join(timeout=600)
+        p.join(timeout=150)
+    for p in procs:
+        if p.is_alive():
+            p.terminate()
     assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
     for r in range(2):
         err, gerr = ret[r]

@@ -1,0 +1,101 @@
+"""The oracle (and, on the GPU, the CUDA path) against fixtures produced by the reference's own in-tree files
+(kgwas/model.py, kgwas/conv.py executed verbatim by oracle/gen_golden_from_reference.py)."""
+import os
+
+import pytest
+import torch
+
+from oracle import kgwas_oracle as O
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+class _Graph:
+    def __init__(self, edge_types):
+        self.edge_types = edge_types
+
+
+def _load(name):
+    return torch.load(os.path.join(GOLD, name), weights_only=True)
+
+
+def _load_state(module, rec):
+    missing, unexpected = module.load_state_dict(rec["state"], strict=False)
+    assert not unexpected and sorted(missing) == sorted(rec["lazy_keys"])
+
+
+def _gat_cases(make_conv, dev):
+    f = _load("ref_gatconv.pt")
+    x_src, x_dst, ei = f["x_src"].to(dev), f["x_dst"].to(dev), f["edge_index"].to(dev)
+    for case in f["cases"]:
+        conv = make_conv((32, 32), **case["kwargs"])
+        _load_state(conv, case)
+        conv = conv.to(dev)
+        out, (ei_out, alpha) = conv((x_src, x_dst), ei, return_attention_weights=True,
+                                    return_raw_attention_weights=case["raw"])
+        assert torch.equal(ei_out.cpu(), f["edge_index"])
+        assert torch.allclose(alpha.cpu(), case["alpha"], rtol=1e-5, atol=1e-6), case["kwargs"]
+        assert torch.allclose(out.cpu(), case["out"], rtol=1e-5, atol=1e-5), case["kwargs"]
+    conv = make_conv(32)
+    _load_state(conv, f["single"])
+    conv = conv.to(dev)
+    out = conv(x_src, f["single"]["edge_index"].to(dev))
+    assert torch.allclose(out.cpu(), f["single"]["out"], rtol=1e-5, atol=1e-5)
+
+
+def _heterognn_case(model_cls, backbone, aggr, dev, tol):
+    f = _load(f"ref_heterognn_{backbone.lower()}_{aggr}.pt")
+    h = f["x"]["SNP"].size(1)
+    ets = list(f["edge_index"].keys())
+    m = model_cls(_Graph(ets), h, 1, 2, backbone, aggr, h, h, h, 1)
+    m({k: v.clone() for k, v in f["x"].items()}, f["edge_index"], 4) if dev == "cpu" else None
+    _load_state(m, f)
+    m = m.to(dev)
+    x = {k: v.to(dev) for k, v in f["x"].items()}
+    ei = {k: v.to(dev) for k, v in f["edge_index"].items()}
+    bs = f["batch_size"]
+    out, hid = m(dict(x), ei, bs, return_h=True)
+    scale = f["out"].abs().max().item()
+    assert (out.cpu() - f["out"]).abs().max().item() <= tol * scale
+    assert torch.allclose(hid.cpu(), f["hidden"], rtol=tol * 10, atol=tol * f["hidden"].abs().max().item())
+    loss = torch.mean(f["w"].to(dev) * (out.reshape(-1) - f["y"].to(dev)) ** 2)
+    assert abs(loss.item() - f["loss"].item()) <= 10 * tol * abs(f["loss"].item())
+    loss.backward()
+    gscale = max(g.abs().max().item() for g in f["grads"].values() if g is not None)
+    params = dict(m.named_parameters())
+    for k, g in f["grads"].items():
+        if g is None:
+            assert params[k].grad is None, k        # relations into unused last-layer outputs get no gradient
+        else:
+            assert params[k].grad is not None, k
+            assert (params[k].grad.cpu() - g).abs().max().item() <= 20 * tol * g.abs().max().item() + 1e-5 * gscale, k
+    if backbone == "GAT":
+        m.zero_grad()
+        o2, att = m(dict(x), ei, bs, return_attention_weights=True)
+        assert (o2.cpu() - f["att_out"]).abs().max().item() <= tol * scale
+        for a, b in zip(att, f["att_mean"]):
+            assert abs(a.item() - b.item()) <= 10 * tol * abs(b.item())
+
+
+def test_oracle_gatconv_matches_reference_conv_py():
+    _gat_cases(lambda ch, **kw: O.GATConv(ch, 32, heads=1, add_self_loops=False, **kw), "cpu")
+
+
+@pytest.mark.parametrize("backbone", ["SAGE", "GAT"])
+@pytest.mark.parametrize("aggr", ["sum", "mean"])
+def test_oracle_heterognn_matches_reference_model_py(backbone, aggr):
+    _heterognn_case(O.HeteroGNN, backbone, aggr, "cpu", 1e-5)
+
+
+@pytest.mark.gpu
+def test_cuda_gatconv_matches_reference_conv_py(cuda):
+    import kgwas_b200
+    _gat_cases(lambda ch, **kw: kgwas_b200.GATConv(ch, 32, heads=1, add_self_loops=False, **kw), cuda)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("backbone", ["SAGE", "GAT"])
+@pytest.mark.parametrize("aggr", ["sum", "mean"])
+def test_cuda_heterognn_matches_reference_model_py(cuda, backbone, aggr):
+    import kgwas_b200
+    _heterognn_case(kgwas_b200.HeteroGNN, backbone, aggr, cuda, 1e-4)
