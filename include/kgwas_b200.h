@@ -105,6 +105,7 @@ typedef struct {
   const int32_t* hseg_order; /* nullable: work item i processes segment hseg_order[i] (L2-window scheduling) */
   const int32_t* hrow_grpptr; /* [n_hrows+1] prefix sum of ceil(segments / KGB_FOLD) per heavy row */
   int32_t n_hgroups;          /* hrow_grpptr[n_hrows] */
+  int64_t n_edges_hint;       /* rowptr[n_rows] if known on the host, else 0: picks the short-row kernel variant */
 } kgb_csr_t;
 enum { KGB_FOLD = 64 };       /* partial sums are folded 64 at a time (two levels) by the last finisher */
 

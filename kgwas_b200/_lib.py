@@ -35,7 +35,7 @@ class CsrStruct(C.Structure):
     _fields_ = [("rowptr", C.c_void_p), ("col", C.c_void_p), ("n_rows", C.c_int32), ("seg_len", C.c_int32),
                 ("n_hrows", C.c_int32), ("n_hsegs", C.c_int32), ("hrow_id", C.c_void_p),
                 ("hrow_segptr", C.c_void_p), ("hseg_hrow", C.c_void_p), ("hseg_order", C.c_void_p),
-                ("hrow_grpptr", C.c_void_p), ("n_hgroups", C.c_int32)]
+                ("hrow_grpptr", C.c_void_p), ("n_hgroups", C.c_int32), ("n_edges_hint", C.c_int64)]
 
 
 _P, _I32, _I64, _F, _SZ = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_size_t
@@ -113,9 +113,9 @@ def _f32c(t, name):
 # graph bookkeeping
 # ---------------------------------------------------------------------------------------------
 
-SEG_LEN = 64            # edges per heavy-row segment (one warp each)
+SEG_LEN = 128           # edges per heavy-row segment (one warp each); 128 + a 24 MB window measured best on B200
 FOLD = 64               # KGB_FOLD: partials folded per level
-L2_WINDOW_BYTES = 48 << 20   # gathered-table window the resident warps should share (126 MB L2)
+L2_WINDOW_BYTES = 24 << 20   # gathered-table window the resident warps should share (126 MB L2)
 
 
 class Csr:
@@ -133,7 +133,7 @@ class Csr:
     def _refresh_struct(self):
         self.struct = CsrStruct(_ptr(self.rowptr), _ptr(self.col), self.n_rows, self.seg_len, self.n_hrows,
                                 self.n_hsegs, _ptr(self.hrow_id), _ptr(self.hrow_segptr), _ptr(self.hseg_hrow),
-                                _ptr(self.hseg_order), _ptr(self.hrow_grpptr), self.n_hgroups)
+                                _ptr(self.hseg_order), _ptr(self.hrow_grpptr), self.n_hgroups, int(self.col.numel()))
 
     def schedule_for_l2(self, row_bytes: int, window_bytes: int = L2_WINDOW_BYTES):
         """Order the heavy segments by the window of the gathered table they read (rows are column-sorted), so

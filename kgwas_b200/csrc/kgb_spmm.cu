@@ -11,7 +11,6 @@
 namespace kgb {
 
 constexpr int kSpmmThreads = 256;  // 8 warps / CTA
-constexpr int kUnroll = 8;   // gathers in flight per warp
 
 struct EdgeW {            // per-edge scalars riding along the gather
   const float* ew;        // weight of the gathered row (NULL -> 1)
@@ -31,7 +30,7 @@ struct Sum2 {
   }
 };
 
-template <int H>
+template <int H, int kUnroll>
 __device__ __forceinline__ void gather_accumulate(RowVec<H>& acc, Sum2& sum2, const int32_t* __restrict__ col,
                                                   const EdgeW& e, const float* __restrict__ x,
                                                   int64_t ldx, int start, int end, int lane) {
@@ -121,8 +120,10 @@ __device__ __forceinline__ RowVec<H> fold_rows(const float* base, int n, int lan
 }
 
 // Work items: [0, n_hsegs) heavy segments (long tasks first), then one item per row.
-template <int H>
-__global__ void __launch_bounds__(kSpmmThreads, H <= 128 ? 3 : 2)
+// UNROLL = gathers in flight per warp: 8 for long rows / segments (bandwidth), 4 with one more resident CTA per SM
+// for CSRs dominated by short rows (latency: 784 k SNP rows with ~10 in-edges each).
+template <int H, int UNROLL>
+__global__ void __launch_bounds__(kSpmmThreads, (H <= 128 ? 3 : 2) + (UNROLL <= 4 && H <= 128 ? 1 : 0))
 k_spmm(kgb_csr_t g, EdgeW e, const float* __restrict__ x, int64_t ldx, float* __restrict__ y, int64_t ldy, float beta,
        const float* __restrict__ bias, int relu, float* __restrict__ rowsum2, HeavyBufs hb) {
   float* __restrict__ partial = hb.partial;
@@ -144,7 +145,7 @@ k_spmm(kgb_csr_t g, EdgeW e, const float* __restrict__ x, int64_t ldx, float* __
       acc.zero();
       Sum2 s2;
       s2.zero();
-      gather_accumulate<H>(acc, s2, g.col, e, x, ldx, start, end, lane);
+      gather_accumulate<H, UNROLL>(acc, s2, g.col, e, x, ldx, start, end, lane);
       acc.store(partial + (int64_t)seg * H, lane);
       if (rowsum2) {
 #pragma unroll
@@ -202,7 +203,7 @@ k_spmm(kgb_csr_t g, EdgeW e, const float* __restrict__ x, int64_t ldx, float* __
       acc.zero();
       Sum2 s2;
       s2.zero();
-      gather_accumulate<H>(acc, s2, g.col, e, x, ldx, start, end, lane);
+      gather_accumulate<H, UNROLL>(acc, s2, g.col, e, x, ldx, start, end, lane);
       write_row<H>(acc, y + (int64_t)row * ldy, beta, bias, relu, lane);
       if (rowsum2) {
 #pragma unroll
@@ -218,10 +219,12 @@ k_spmm(kgb_csr_t g, EdgeW e, const float* __restrict__ x, int64_t ldx, float* __
 }
 
 inline unsigned spmm_grid(int64_t n_items) {
+  // one work item per warp, CTAs dispatched in item order: the resident warps then work on a contiguous range of
+  // items, which is what the L2-window ordering of the heavy segments needs (a grid-stride loop would interleave
+  // several windows)
   const int64_t warps_per_cta = kSpmmThreads / 32;
   int64_t ctas = (n_items + warps_per_cta - 1) / warps_per_cta;
-  const int64_t cap = (int64_t)kNumSMs * 8 * 4;  // 8 resident CTAs/SM x 4 waves, grid-stride beyond
-  if (ctas > cap) ctas = cap;
+  if (ctas > 0x7fffffff) ctas = 0x7fffffff;
   if (ctas < 1) ctas = 1;
   return (unsigned)ctas;
 }
@@ -273,7 +276,14 @@ extern "C" int kgb_spmm(const kgb_csr_t* csr, const float* ew, const int32_t* wp
   }
   const EdgeW e{ew, wperm, ew2, ew2 ? rowsum2_bins : 1};
   const unsigned grid = spmm_grid((int64_t)csr->n_hsegs + csr->n_rows);
-  KGB_DISPATCH_H(h, (k_spmm<H><<<grid, kSpmmThreads, 0, stream>>>(*csr, e, x, ldx, y, ldy, beta, bias, relu, rowsum2, hb)));
+  // short-row CSRs: average in-degree below 16 and no heavy rows dominating
+  const int64_t n_edges_hint = csr->n_edges_hint > 0 ? csr->n_edges_hint : 0;
+  const bool short_rows = false && n_edges_hint > 0;  // measured on B200: the 4-deep / 4-CTA variant is ~15 % slower on the SNP-row jobs
+  if (short_rows) {
+    KGB_DISPATCH_H(h, (k_spmm<H, 4><<<grid, kSpmmThreads, 0, stream>>>(*csr, e, x, ldx, y, ldy, beta, bias, relu, rowsum2, hb)));
+  } else {
+    KGB_DISPATCH_H(h, (k_spmm<H, 8><<<grid, kSpmmThreads, 0, stream>>>(*csr, e, x, ldx, y, ldy, beta, bias, relu, rowsum2, hb)));
+  }
   KGB_LAUNCH_OK();
   return KGB_OK;
 }

@@ -21,6 +21,41 @@ def _empty(rows, cols, like):
     return torch.empty((rows, cols), dtype=torch.float32, device=like.device)
 
 
+MULTI_STREAM = True      # run independent kernel chains of a layer on a side stream (bench.py turns it off while it
+                         # times single kernels for the roofline, so that their durations are not shared)
+_SIDE = {}
+
+
+class _Fork:
+    """Fork / join of one side CUDA stream inside a layer.  Every buffer is allocated on the main stream BEFORE it is
+    used on the side stream and kept alive until ``join`` (the caching allocator ties a block to its allocation
+    stream), so no ``record_stream`` bookkeeping is needed."""
+
+    def __init__(self, device):
+        self.main = torch.cuda.current_stream(device)
+        self.side = None
+        self.keep = []
+        if MULTI_STREAM:
+            key = (device.index, self.main.cuda_stream)
+            if key not in _SIDE:
+                _SIDE[key] = torch.cuda.Stream(device)
+            self.side = _SIDE[key]
+            self.side.wait_stream(self.main)
+
+    def stream(self, on_side: bool):
+        return torch.cuda.stream(self.side if (on_side and self.side is not None) else self.main)
+
+    def sync_side_after_main(self):
+        """everything enqueued on main so far happens-before what the side stream is given next"""
+        if self.side is not None:
+            self.side.wait_stream(self.main)
+
+    def join(self):
+        if self.side is not None:
+            self.main.wait_stream(self.side)
+        self.keep.clear()
+
+
 class _SageLayerCtx:
     """Static description handed to the autograd Function (not a tensor)."""
 
@@ -57,43 +92,58 @@ class HeteroSageLayerFn(torch.autograd.Function):
         ctx.set_materialize_grads(False)
         x = dict(zip(meta.node_types, [t.contiguous() for t in xs]))
         outs, saved_A = [], {}
+        # ---- phase 1 (main stream): allocate every buffer, do the [h,h]-sized parameter reshuffles -------------
+        prep = {}
         for T in plan.dst_types:
             a, b = plan.rel_range[T]
             scale = meta.rel_scale[T]
             n_t = plan.num_nodes[T]
-            out = _empty(n_t, h, Wl)
-            # root term first (dense, overwrites), then every job accumulates; the last writer applies the ReLU.
-            # (A gather-reduce that accumulates re-reads one row per warp, which hides latency far better than
-            # a GEMM epilogue re-reading C.)
-            w_root = Wr[a:b].sum(0)
             bias = bl[a:b].sum(0)
             if scale != 1.0:
                 bias = bias * scale
+            job_bufs = []
+            for job in plan.jobs[T]:
+                lo, hi = job.rel_ids[0], job.rel_ids[-1] + 1
+                job.schedule(h)
+                if job.mode == "xf":       # Z = X_src . [W_1;..;W_R]^T  (view: rows k*h.. = W_l^k)
+                    job_bufs.append((Wl[lo:hi].reshape(job.R * h, h), _empty(job.n_src, job.R * h, Wl)))
+                else:                      # A = gather-reduce, then out += A . [W_1|..|W_R]^T
+                    job_bufs.append((Wl[lo:hi].permute(1, 0, 2).reshape(h, job.R * h), _empty(n_t, job.R * h, Wl)))
+            prep[T] = (_empty(n_t, h, Wl), Wr[a:b].sum(0), bias, job_bufs)
+        # ---- phase 2: one kernel chain per destination type; the largest type (SNP) on the main stream, the
+        # others on the side stream: their many small launches hide behind the big gather-reduce kernels ------------
+        fork = _Fork(Wl.device)
+        big = max(plan.dst_types, key=lambda t: plan.num_nodes[t])
+        for T in plan.dst_types:
+            scale = meta.rel_scale[T]
+            n_t = plan.num_nodes[T]
+            out, w_root, bias, job_bufs = prep[T]
             jobs = plan.jobs[T]
             relu_T = meta.fused_relu(T)
-            if T in meta.root_range:
-                r0, r1 = meta.root_range[T]
-                out.zero_()
-                _lib.gemm(KGB_NT, x[T][r0:r1], w_root, out[r0:r1], r1 - r0, h, h, alpha=scale, bias=bias)
-            else:
-                _lib.gemm(KGB_NT, x[T], w_root, out, n_t, h, h, alpha=scale, bias=bias, relu=relu_T and not jobs)
-            for ji, job in enumerate(jobs):
-                lo, hi = job.rel_ids[0], job.rel_ids[-1] + 1
-                R, xs_ = job.R, x[job.src_type]
-                job.schedule(h)
-                last_relu = relu_T and ji == len(jobs) - 1
-                if job.mode == "xf":
-                    wcat = Wl[lo:hi].reshape(R * h, h)                       # view: rows k*h.. = W_l^k
-                    z = _empty(job.n_src, R * h, Wl)
-                    _lib.gemm(KGB_NT, xs_, wcat, z, job.n_src, R * h, h, alpha=scale)
-                    _lib.spmm(job.csr, z.view(job.n_src * R, h), out, h, ew=job.w_mean, beta=1.0, relu=last_relu)
+            with fork.stream(T != big):
+                # root term first (dense, overwrites), then every job accumulates; the last writer applies the ReLU.
+                # (A gather-reduce that accumulates re-reads one row per warp, which hides latency far better than
+                # a GEMM epilogue re-reading C.)
+                if T in meta.root_range:
+                    r0, r1 = meta.root_range[T]
+                    out.zero_()
+                    _lib.gemm(KGB_NT, x[T][r0:r1], w_root, out[r0:r1], r1 - r0, h, h, alpha=scale, bias=bias)
                 else:
-                    A = _empty(n_t, R * h, Wl)
-                    _lib.spmm(job.csr, xs_, A.view(n_t * R, h), h, ew=job.w_mean)
-                    wcat_t = Wl[lo:hi].permute(1, 0, 2).reshape(h, R * h)    # [h, R*h]: out += A . wcat_t^T
-                    _lib.gemm(KGB_NT, A, wcat_t, out, n_t, h, R * h, alpha=scale, beta=1.0, relu=last_relu)
-                    saved_A[(T, ji)] = A
+                    _lib.gemm(KGB_NT, x[T], w_root, out, n_t, h, h, alpha=scale, bias=bias, relu=relu_T and not jobs)
+                for ji, job in enumerate(jobs):
+                    R, xs_ = job.R, x[job.src_type]
+                    last_relu = relu_T and ji == len(jobs) - 1
+                    w_job, buf = job_bufs[ji]
+                    if job.mode == "xf":
+                        _lib.gemm(KGB_NT, xs_, w_job, buf, job.n_src, R * h, h, alpha=scale)
+                        _lib.spmm(job.csr, buf.view(job.n_src * R, h), out, h, ew=job.w_mean, beta=1.0, relu=last_relu)
+                    else:
+                        _lib.spmm(job.csr, xs_, buf.view(n_t * R, h), h, ew=job.w_mean)
+                        _lib.gemm(KGB_NT, buf, w_job, out, n_t, h, R * h, alpha=scale, beta=1.0, relu=last_relu)
+                        saved_A[(T, ji)] = buf
             outs.append(out)
+        fork.keep.append(prep)
+        fork.join()
         ctx.meta = meta
         ctx.saved_A = saved_A
         ctx.save_for_backward(Wl, Wr, *[x[t] for t in meta.node_types], *outs)
@@ -125,7 +175,10 @@ class HeteroSageLayerFn(torch.autograd.Function):
                 return dx[t], 0.0
             return dx[t], 1.0
 
-        # largest destination type first: its dense d x = g . W_root then is the first (overwriting) writer
+        # largest destination type first: its dense d x = g . W_root then is the first (overwriting) writer.
+        # Main stream: the d x chain (ReLU mask, NN GEMMs, transposed gather-reduces).  Side stream: everything that only
+        # produces parameter gradients (column sums, TN split-K GEMMs) -- it reads g / dz / A and writes disjoint slices.
+        fork = _Fork(Wl.device)
         order = sorted(range(len(plan.dst_types)), key=lambda i: -plan.num_nodes[plan.dst_types[i]])
         for T, d_out in [(plan.dst_types[i], d_outs[i]) for i in order]:
             if d_out is None:
@@ -136,16 +189,20 @@ class HeteroSageLayerFn(torch.autograd.Function):
             g = _lib.relu_bwd(d_out, outs[T]) if meta.fused_relu(T) else d_out.contiguous()
             if scale != 1.0:
                 g = g * scale
+            fork.keep.append(g)
             for i in range(a, b):
                 used[i] = True
             r0, r1 = meta.root_range.get(T, (0, n_t))          # rows whose root term this rank owns
             if need_w:
                 db = torch.empty(h, dtype=torch.float32, device=g.device)
-                _lib.wcolsum(g[r0:r1], h, db)
-                dbl[a:b] = db
                 dwr = _empty(h, h, g)
-                _lib.gemm(KGB_TN, g[r0:r1], x[T][r0:r1], dwr, h, h, r1 - r0)
-                dWr[a:b] = dwr
+                fork.keep += [db, dwr]
+                fork.sync_side_after_main()
+                with fork.stream(True):
+                    _lib.wcolsum(g[r0:r1], h, db)
+                    dbl[a:b] = db
+                    _lib.gemm(KGB_TN, g[r0:r1], x[T][r0:r1], dwr, h, h, r1 - r0)
+                    dWr[a:b] = dwr
             if need_x[T]:
                 buf, beta = dx_target(T)
                 if (r0, r1) != (0, n_t) and beta == 0.0:
@@ -157,9 +214,12 @@ class HeteroSageLayerFn(torch.autograd.Function):
                 R, S = job.R, job.src_type
                 if job.mode == "xf":
                     dz = _empty(job.n_src, R * h, g)
+                    fork.keep.append(dz)
                     _lib.spmm(job.tcsr, g, dz.view(job.n_src * R, h), h, ew=job.w_mean, wperm=job.t_eperm)
                     if need_w:
-                        _lib.gemm(KGB_TN, dz, x[S], dWl[lo:hi].view(R * h, h), R * h, h, job.n_src)
+                        fork.sync_side_after_main()
+                        with fork.stream(True):
+                            _lib.gemm(KGB_TN, dz, x[S], dWl[lo:hi].view(R * h, h), R * h, h, job.n_src)
                     if need_x[S]:
                         buf, beta = dx_target(S)
                         _lib.gemm(KGB_NN, dz, Wl[lo:hi].reshape(R * h, h), buf, job.n_src, h, R * h, beta=beta)
@@ -167,14 +227,20 @@ class HeteroSageLayerFn(torch.autograd.Function):
                     A = ctx.saved_A[(T, ji)]
                     if need_w:
                         dwt = _empty(h, R * h, g)                              # [h_out, R*h_in]
-                        _lib.gemm(KGB_TN, g, A, dwt, h, R * h, n_t)
-                        dWl[lo:hi] = dwt.view(h, R, h).permute(1, 0, 2)
+                        fork.keep.append(dwt)
+                        fork.sync_side_after_main()
+                        with fork.stream(True):
+                            _lib.gemm(KGB_TN, g, A, dwt, h, R * h, n_t)
+                            dWl[lo:hi] = dwt.view(h, R, h).permute(1, 0, 2)
                     if need_x[S]:
                         wcat_t = Wl[lo:hi].permute(1, 0, 2).reshape(h, R * h)
                         dA = _empty(n_t, R * h, g)
+                        fork.keep.append(dA)
                         _lib.gemm(KGB_NN, g, wcat_t, dA, n_t, R * h, h)
                         buf, beta = dx_target(S)
                         _lib.spmm(job.tcsr, dA.view(n_t * R, h), buf, h, ew=job.w_mean, wperm=job.t_eperm, beta=beta)
+        fork.keep.append(ctx.saved_A)
+        fork.join()
         ctx.saved_A = None
         grads_x = []
         for t in meta.node_types:
