@@ -99,3 +99,28 @@ def test_tc_accuracy_is_fp32_class(cuda):
         torch.backends.cuda.matmul.allow_tf32 = old
     assert ours < tf32 / 2.5, (ours, tf32)     # same-sign data: both are dominated by accumulator truncation
     assert ours / ref.abs().max().item() < TOL
+
+
+@pytest.mark.parametrize("layout", ["NT", "NN"])
+@pytest.mark.parametrize("m,n,k", [(784256, 128, 128), (70001, 128, 128), (100000, 64, 64), (65536, 32, 128), (300000, 128, 32)])
+def test_tc_row_streaming_kernel(cuda, layout, m, n, k):
+    """Persistent node-row GEMM (resident weights, two TMEM accumulator sets): ragged last tile, narrow N / K,
+    epilogue options, and repeatability."""
+    from kgwas_b200 import _lib
+    torch.manual_seed(m + n + k)
+    a = torch.randn(m, k, device=cuda)
+    b = torch.randn(n, k, device=cuda) if layout == "NT" else torch.randn(k, n, device=cuda)
+    lay = _lib.KGB_NT if layout == "NT" else _lib.KGB_NN
+    ref = a.double() @ (b.double().T if layout == "NT" else b.double())
+    c = torch.full((m, n), float("nan"), device=cuda)
+    _lib.gemm(lay, a, b, c, m, n, k)
+    assert _err(c, ref, k) < TOL, _err(c, ref, k)
+    bias = torch.randn(n, device=cuda)
+    c0 = torch.randn(m, n, device=cuda)
+    c2 = c0.clone()
+    _lib.gemm(lay, a, b, c2, m, n, k, alpha=0.5, beta=1.0, bias=bias, relu=True)
+    ref2 = (0.5 * ref + c0.double() + bias.double()).clamp(min=0)
+    assert _err(c2, ref2, k) < TOL
+    c3 = torch.empty(m, n, device=cuda)
+    _lib.gemm(lay, a, b, c3, m, n, k)
+    assert torch.equal(c, c3)
