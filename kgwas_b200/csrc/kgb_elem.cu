@@ -54,13 +54,16 @@ k_wcolsum_stage1(const float* __restrict__ x, int64_t ldx, const float* __restri
     }
   }
 }
-// stage 2: out[r][c] = beta*out + sum_b part[b][r][c]   (chunk order)
+// stage 2: out[i] = beta*out[i] + sum_b part[b][i].  One warp per output element: lanes stride over the chunks
+// (fixed lane <-> chunk mapping, fixed shuffle tree => deterministic), 8 outputs per CTA.
 __global__ void k_wcolsum_stage2(const float* __restrict__ part, int n_ctas, int RH, float* __restrict__ out, float beta) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (i >= RH) return;
   float s = 0.f;
-  for (int b = 0; b < n_ctas; ++b) s += part[(int64_t)b * RH + i];
-  out[i] = (beta != 0.f ? beta * out[i] : 0.f) + s;
+  for (int b = lane; b < n_ctas; b += 32) s += part[(int64_t)b * RH + i];
+  s = warp_sum(s);
+  if (lane == 0) out[i] = (beta != 0.f ? beta * out[i] : 0.f) + s;
 }
 
 // a[i, s] = <x[i, s*slot_stride : +h], v[s, :]>
@@ -171,7 +174,7 @@ extern "C" int kgb_wcolsum(const float* x, int64_t ldx, const float* w, int64_t 
 #undef KGB_WCS
   KGB_LAUNCH_OK();
   const int RH = n_slots * h;
-  k_wcolsum_stage2<<<(RH + 255) / 256, 256, 0, stream>>>(part, (int)ctas, RH, out, beta);
+  k_wcolsum_stage2<<<(RH + 7) / 8, 256, 0, stream>>>(part, (int)ctas, RH, out, beta);
   KGB_LAUNCH_OK();
   return KGB_OK;
 }

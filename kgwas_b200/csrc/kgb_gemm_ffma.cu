@@ -130,23 +130,48 @@ k_gemm_ffma(const float* __restrict__ a, int64_t lda, const float* __restrict__ 
   }
 }
 
-// C = act(alpha * sum_z part[z] + beta*C + bias), summed in slice order (deterministic)
-__global__ void k_splitk_reduce(const float* __restrict__ part, int splits, int64_t M, int64_t N, float* __restrict__ c,
-                                int64_t ldc, float alpha, float beta, const float* __restrict__ bias, int relu) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // float4 index
+// C = act(alpha * sum_z part[z] + beta*C + bias).  256 threads = 64 float4 outputs x 4 slice lanes: lane q sums the
+// slices z = q, q+4, ... (4 loads in flight), the 4 lane sums are folded in lane order => deterministic.
+__global__ void __launch_bounds__(256)
+k_splitk_reduce(const float* __restrict__ part, int splits, int64_t M, int64_t N, float* __restrict__ c,
+                int64_t ldc, float alpha, float beta, const float* __restrict__ bias, int relu) {
+  __shared__ float4 red[4][64];
+  const int o = threadIdx.x & 63, q = threadIdx.x >> 6;
+  const int64_t i = (int64_t)blockIdx.x * 64 + o;  // float4 index
   const int64_t nq = N / 4;
-  if (i >= M * nq) return;
-  const int64_t m = i / nq, n = (i % nq) * 4;
+  const bool live = i < M * nq;
+  const int64_t m = live ? i / nq : 0, n = live ? (i % nq) * 4 : 0;
   float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int z = 0; z < splits; ++z) {
-    const float4 p = *reinterpret_cast<const float4*>(part + ((int64_t)z * M + m) * N + n);
-    s.x += p.x; s.y += p.y; s.z += p.z; s.w += p.w;
+  if (live) {
+    const float* p = part + m * N + n;
+    const int64_t zs = M * N;
+    int z = q;
+    for (; z + 12 < splits; z += 16) {
+      const float4 p0 = *reinterpret_cast<const float4*>(p + (int64_t)z * zs);
+      const float4 p1 = *reinterpret_cast<const float4*>(p + (int64_t)(z + 4) * zs);
+      const float4 p2 = *reinterpret_cast<const float4*>(p + (int64_t)(z + 8) * zs);
+      const float4 p3 = *reinterpret_cast<const float4*>(p + (int64_t)(z + 12) * zs);
+      s.x += p0.x; s.y += p0.y; s.z += p0.z; s.w += p0.w;
+      s.x += p1.x; s.y += p1.y; s.z += p1.z; s.w += p1.w;
+      s.x += p2.x; s.y += p2.y; s.z += p2.z; s.w += p2.w;
+      s.x += p3.x; s.y += p3.y; s.z += p3.z; s.w += p3.w;
+    }
+    for (; z < splits; z += 4) {
+      const float4 p0 = *reinterpret_cast<const float4*>(p + (int64_t)z * zs);
+      s.x += p0.x; s.y += p0.y; s.z += p0.z; s.w += p0.w;
+    }
   }
+  red[q][o] = s;
+  __syncthreads();
+  if (q != 0 || !live) return;
+  s = red[0][o];
+#pragma unroll
+  for (int k = 1; k < 4; ++k) { s.x += red[k][o].x; s.y += red[k][o].y; s.z += red[k][o].z; s.w += red[k][o].w; }
   s.x *= alpha; s.y *= alpha; s.z *= alpha; s.w *= alpha;
   float* cp = c + m * ldc + n;
   if (beta != 0.f) {
-    const float4 o = *reinterpret_cast<const float4*>(cp);
-    s.x = fmaf(beta, o.x, s.x); s.y = fmaf(beta, o.y, s.y); s.z = fmaf(beta, o.z, s.z); s.w = fmaf(beta, o.w, s.w);
+    const float4 o4 = *reinterpret_cast<const float4*>(cp);
+    s.x = fmaf(beta, o4.x, s.x); s.y = fmaf(beta, o4.y, s.y); s.z = fmaf(beta, o4.z, s.z); s.w = fmaf(beta, o4.w, s.w);
   }
   if (bias) { s.x += bias[n]; s.y += bias[n + 1]; s.z += bias[n + 2]; s.w += bias[n + 3]; }
   if (relu) { s.x = fmaxf(s.x, 0.f); s.y = fmaxf(s.y, 0.f); s.z = fmaxf(s.z, 0.f); s.w = fmaxf(s.w, 0.f); }
@@ -192,7 +217,7 @@ int gemm_ffma(int layout, const float* a, int64_t lda, const float* b, int64_t l
       k_gemm_ffma<KGB_TN, true><<<grid, GT, 0, stream>>>(a, lda, b, ldb, c, ldc, M, N, K, alpha, beta, bias, relu, part, kps);
       KGB_LAUNCH_OK();
       const int64_t n4 = M * N / 4;
-      k_splitk_reduce<<<(unsigned)((n4 + 255) / 256), 256, 0, stream>>>(part, (int)grid.z, M, N, c, ldc, alpha, beta, bias, relu);
+      k_splitk_reduce<<<(unsigned)((n4 + 63) / 64), 256, 0, stream>>>(part, (int)grid.z, M, N, c, ldc, alpha, beta, bias, relu);
     }
   }
   KGB_LAUNCH_OK();

@@ -540,7 +540,7 @@ __global__ void k_splitk_reduce(const float* __restrict__ part, int splits, int6
 
 static int tc_splits(int64_t m, int64_t n, int64_t k) {
   const int64_t tiles = ((m + tc::TM - 1) / tc::TM) * ((n + tc::TN_ - 1) / tc::TN_);
-  int64_t s = (4 * kNumSMs + tiles - 1) / tiles;
+  int64_t s = (2 * kNumSMs + tiles - 1) / tiles;       // two resident CTAs per SM
   const int64_t max_s = (k + 16 * tc::BK - 1) / (16 * tc::BK);  // at least 256 k per slice
   if (s > max_s) s = max_s;
   return (int)(s < 1 ? 1 : s);
@@ -614,7 +614,7 @@ int gemm_tc(int layout, const float* a, int64_t lda, const float* b, int64_t ldb
                                                                            bias, relu, part, kps);
       KGB_LAUNCH_OK();
       const int64_t n4 = M * N / 4;
-      k_splitk_reduce<<<(unsigned)((n4 + 255) / 256), 256, 0, stream>>>(part, (int)grid.z, M, N, c, ldc, alpha, beta, bias,
+      k_splitk_reduce<<<(unsigned)((n4 + 63) / 64), 256, 0, stream>>>(part, (int)grid.z, M, N, c, ldc, alpha, beta, bias,
                                                                         relu);
     }
   }

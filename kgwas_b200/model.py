@@ -26,6 +26,39 @@ class SimpleMLP(nn.Module):
         return self.FC_output(h)
 
 
+class _HeadFn(torch.autograd.Function):
+    """logit[i] = <h[i,:], w> + b  for the single-output head."""
+
+    @staticmethod
+    def forward(ctx, hid, w, b):
+        from . import _lib
+        hid = hid.contiguous()
+        out = torch.empty((hid.size(0), 1), dtype=torch.float32, device=hid.device)
+        _lib.rowdot(hid, w, out, w.size(1), 1, 0)
+        if b is not None:
+            out += b
+        ctx.save_for_backward(hid, w)
+        ctx.has_bias = b is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        from . import _lib
+        hid, w = ctx.saved_tensors
+        g = g.contiguous()
+        hdim = w.size(1)
+        d_hid = d_w = d_b = None
+        if ctx.needs_input_grad[0]:
+            d_hid = torch.empty_like(hid)
+            _lib.rank_update(g, w, d_hid, hdim, 1, 0.0)
+        if ctx.needs_input_grad[1]:
+            d_w = torch.empty_like(w)
+            _lib.wcolsum(hid, hdim, d_w, w=g, n_slots=1)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            d_b = g.sum(0)
+        return d_hid, d_w, d_b
+
+
 class HeteroGNN(nn.Module):
     def __init__(self, pyg_data, hidden_channels, out_channels, num_layers, gnn_backbone, gnn_aggr,
                  snp_init_dim_size, gene_init_dim_size, go_init_dim_size, gat_num_head, no_relu=False):
@@ -63,7 +96,10 @@ class HeteroGNN(nn.Module):
         return out
 
     def head(self, h_snp):
-        # out_channels is 1 in KGWAS: a [N,h].[h,1] product is a GEMV -- left to torch
+        """``self.lin`` (model.py:50,83-86).  KGWAS uses out_channels = 1: a row-dot per SNP, run by kgb_rowdot /
+        kgb_rank_update / kgb_wcolsum; other widths go through torch (plain library GEMM)."""
+        if self.lin.weight.size(0) == 1 and h_snp.is_cuda and h_snp.dtype == torch.float32:
+            return _HeadFn.apply(h_snp, self.lin.weight, self.lin.bias)
         return torch.nn.functional.linear(h_snp, self.lin.weight, self.lin.bias)
 
     def forward(self, x_dict, edge_index_dict, batch_size, genotype=None, return_h=False,
