@@ -77,13 +77,19 @@ class ShardContext:
             _plan.DEG_REDUCE = prev
 
     def combine(self, out: Dict[str, torch.Tensor], relu: bool) -> Dict[str, torch.Tensor]:
-        res = {}
-        for t, v in out.items():
-            if t in self.root_range:
-                v = all_reduce_sum(v)
-                if relu:
-                    v = v.relu()
-            res[t] = v
+        """One all-reduce per layer and direction: the partial rows of all shared node types travel as one flat
+        buffer (~22 MB at h=128), then the ReLU runs on the summed rows."""
+        shared = [t for t in out if t in self.root_range]
+        res = dict(out)
+        if shared:
+            flat = all_reduce_sum(torch.cat([out[t].reshape(-1) for t in shared]))
+            if relu:
+                flat = flat.relu()
+            off = 0
+            for t in shared:
+                n = out[t].numel()
+                res[t] = flat[off:off + n].view_as(out[t])
+                off += n
         return res
 
 
@@ -135,10 +141,8 @@ def all_reduce_gradients(params):
         return
     flat = torch.cat([g.reshape(-1) for g in grads])
     dist.all_reduce(flat, op=dist.ReduceOp.SUM)
-    off = 0
-    for g in grads:
-        g.copy_(flat[off:off + g.numel()].view_as(g))
-        off += g.numel()
+    views = [v.view_as(g) for v, g in zip(flat.split([g.numel() for g in grads]), grads)]
+    torch._foreach_copy_(grads, views)          # one fused multi-tensor copy instead of ~200 small launches
 
 
 # -------------------------------------------------------------------------------------------------
