@@ -89,6 +89,9 @@ KGB_API int kgb_csr_heavy_fill(const int32_t* rowptr, int32_t n_rows, int32_t se
  * kgwas/model.py:38; mean = precomputed 1/deg edge weights) and `alpha.unsqueeze(-1) * x_j` +
  * 'add' aggregation of GATConv (kgwas/conv.py:227-228, :54); run on the transposed CSR (with
  * wperm = t_eperm so the weights stay in CSR order) it is their backward (index_add / gather).
+ * dot_w [h] / dot_out [n_rows] (both or neither): dot_out[i] = <y[i,:], dot_w> of the row just
+ * written -- the single-output head `self.lin` applied to the ReLU-ed SNP rows (kgwas/model.py:50,
+ * 83-86) without a second pass over the [N_SNP, h] tensor.
  * heavy_* come from kgb_csr_heavy_*; pass n_hrows = n_hsegs = 0 when no row exceeds seg_len.
  * scratch: kgb_spmm_scratch_bytes(), zero-initialised ONCE by the caller (the kernel leaves its
  * ticket counters zero again on exit); may be NULL when n_hsegs == 0. */
@@ -106,6 +109,9 @@ typedef struct {
   const int32_t* hrow_grpptr; /* [n_hrows+1] prefix sum of ceil(segments / KGB_FOLD) per heavy row */
   int32_t n_hgroups;          /* hrow_grpptr[n_hrows] */
   int64_t n_edges_hint;       /* rowptr[n_rows] if known on the host, else 0: picks the short-row kernel variant */
+  const int32_t* hitem;       /* nullable [n_hsegs][4]: work item i = (first slot, slot count, segment id, heavy-row
+                                 slot) in hseg_order order -- everything a warp needs to start a segment in ONE
+                                 16-byte load (the lean kernel needs it when n_hsegs > 0) */
 } kgb_csr_t;
 enum { KGB_FOLD = 64 };       /* partial sums are folded 64 at a time (two levels) by the last finisher */
 
@@ -113,8 +119,9 @@ KGB_API size_t kgb_spmm_scratch_bytes(int32_t n_hrows, int32_t n_hsegs, int32_t 
 enum { KGB_MAX_BINS = 8 };
 KGB_API int kgb_spmm(const kgb_csr_t* csr, const float* ew, const int32_t* wperm, const float* ew2,
                      float* rowsum2, int32_t rowsum2_bins, const float* x, int64_t ldx, float* y,
-                     int64_t ldy, int32_t h, float beta, const float* bias, int32_t relu, void* scratch,
-                     size_t scratch_bytes, kgb_stream_t stream);
+                     int64_t ldy, int32_t h, float beta, const float* bias, int32_t relu,
+                     const float* dot_w, float* dot_out, void* scratch, size_t scratch_bytes,
+                     kgb_stream_t stream);
 
 /* ---- dense contractions ([nodes x in] . [in x out]) ------------------------------- */
 /* C[M,N] = act( alpha * op(A).op(B) + beta*C + bias[N] )      (row-major, strides in floats)
@@ -135,6 +142,20 @@ KGB_API int kgb_gemm(int32_t layout, const float* a, int64_t lda, const float* b
 /* ---- small fused elementwise / reduction helpers ---------------------------------- */
 /* g[i] = dy[i] * (y[i] > 0)          backward of `x.relu()` (kgwas/model.py:75)          */
 KGB_API int kgb_relu_bwd(const float* dy, const float* y, float* g, int64_t n, kgb_stream_t stream);
+/* Backward through the fused ReLU of a layer output, the single-output head, and the bias
+ * column sums, in ONE pass over the [m, h] rows (autograd of kgwas/model.py:75,83-86 plus the
+ * lin_l.bias gradient of every relation into this node type):
+ *   g[i,:]    = scale * (y[i,:] > 0) * ( dy[i,:] + dp[i] * wv[:] )     dy, dp nullable (not both);
+ *                                                                       y nullable (no mask)
+ *   sums[0,:] = sum_i g[i,:]                                            (bias gradient)
+ *   sums[1,:] = sum_i dp[i] * y[i,:]                                    (head weight gradient; needs dp, y)
+ * sums is [2, h] (nullable).  Two-stage deterministic reduction; workspace from
+ * kgb_relu_bwd_fused_workspace_bytes(). */
+KGB_API size_t kgb_relu_bwd_fused_workspace_bytes(int64_t m, int32_t h);
+KGB_API int kgb_relu_bwd_fused(const float* dy, int64_t lddy, const float* y, int64_t ldy,
+                               const float* dp, const float* wv, float scale, float* g, int64_t ldg,
+                               int64_t m, int32_t h, float* sums, void* workspace,
+                               size_t workspace_bytes, kgb_stream_t stream);
 /* out[s, :] = beta*out[s, :] + sum_m w[m, s] * x[m, :]   (w NULL -> plain column sum, n_slots 1)
  * db_l of SAGEConv.lin_l / GATConv.bias, and d(att-folded vectors) of GATConv. */
 KGB_API size_t kgb_wcolsum_workspace_bytes(int64_t m, int32_t n_slots, int32_t h);

@@ -35,7 +35,8 @@ class CsrStruct(C.Structure):
     _fields_ = [("rowptr", C.c_void_p), ("col", C.c_void_p), ("n_rows", C.c_int32), ("seg_len", C.c_int32),
                 ("n_hrows", C.c_int32), ("n_hsegs", C.c_int32), ("hrow_id", C.c_void_p),
                 ("hrow_segptr", C.c_void_p), ("hseg_hrow", C.c_void_p), ("hseg_order", C.c_void_p),
-                ("hrow_grpptr", C.c_void_p), ("n_hgroups", C.c_int32), ("n_edges_hint", C.c_int64)]
+                ("hrow_grpptr", C.c_void_p), ("n_hgroups", C.c_int32), ("n_edges_hint", C.c_int64),
+                ("hitem", C.c_void_p)]
 
 
 _P, _I32, _I64, _F, _SZ = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_size_t
@@ -52,8 +53,8 @@ SIGNATURES = {
     "kgb_csr_heavy_workspace_bytes": (_SZ, [_I32]),
     "kgb_csr_heavy_fill": (C.c_int, [_P, _I32, _I32, _I32, _I32, _P, _P, _P, _P, _SZ, _P]),
     "kgb_spmm_scratch_bytes": (_SZ, [_I32, _I32, _I32, _I32]),
-    "kgb_spmm": (C.c_int, [C.POINTER(CsrStruct), _P, _P, _P, _P, _I32, _P, _I64, _P, _I64, _I32, _F, _P, _I32, _P, _SZ,
-                           _P]),
+    "kgb_spmm": (C.c_int, [C.POINTER(CsrStruct), _P, _P, _P, _P, _I32, _P, _I64, _P, _I64, _I32, _F, _P, _I32, _P, _P,
+                           _P, _SZ, _P]),
     "kgb_gat_scratch_bytes": (_SZ, [_I32, _I32]),
     "kgb_gat_alpha": (C.c_int, [C.POINTER(CsrStruct), _P, _P, _I32, _I32, _P, _F, _F, _I32, _P, _SZ, _P]),
     "kgb_sddmm": (C.c_int, [C.POINTER(CsrStruct), _P, _I64, _P, _I64, _I32, _P, _P]),
@@ -62,6 +63,8 @@ SIGNATURES = {
     "kgb_gemm_workspace_bytes": (_SZ, [_I32, _I64, _I64, _I64]),
     "kgb_gemm": (C.c_int, [_I32, _P, _I64, _P, _I64, _P, _I64, _I64, _I64, _I64, _F, _F, _P, _I32, _P, _SZ, _P]),
     "kgb_relu_bwd": (C.c_int, [_P, _P, _P, _I64, _P]),
+    "kgb_relu_bwd_fused_workspace_bytes": (_SZ, [_I64, _I32]),
+    "kgb_relu_bwd_fused": (C.c_int, [_P, _I64, _P, _I64, _P, _P, _F, _P, _I64, _I64, _I32, _P, _P, _SZ, _P]),
     "kgb_wcolsum_workspace_bytes": (_SZ, [_I64, _I32, _I32]),
     "kgb_wcolsum": (C.c_int, [_P, _I64, _P, _I64, _I64, _I32, _I32, _P, _F, _P, _SZ, _P]),
     "kgb_rowdot": (C.c_int, [_P, _I64, _I64, _I32, _I32, _I64, _P, _P, _I64, _P]),
@@ -127,13 +130,24 @@ class Csr:
         self.hrow_id = self.hrow_segptr = self.hseg_hrow = self.hrow_grpptr = None
         self._scratch = {}
         self.hseg_order = None
+        self.hitem = None
         self._build_heavy()
         self._refresh_struct()
 
     def _refresh_struct(self):
+        if self.n_hsegs > 0:
+            # one 16-byte record per heavy work item, in scheduling order: (first slot, slot count, segment, heavy row)
+            order = self.hseg_order.long() if self.hseg_order is not None else \
+                torch.arange(self.n_hsegs, device=self.rowptr.device)
+            hr = self.hseg_hrow.long()[order]
+            row = self.hrow_id.long()[hr]
+            start = self.rowptr.long()[row] + (order - self.hrow_segptr.long()[hr]) * self.seg_len
+            length = torch.minimum(self.rowptr.long()[row + 1] - start, torch.full_like(start, self.seg_len))
+            self.hitem = torch.stack([start, length, order, hr], dim=1).to(torch.int32).contiguous()
         self.struct = CsrStruct(_ptr(self.rowptr), _ptr(self.col), self.n_rows, self.seg_len, self.n_hrows,
                                 self.n_hsegs, _ptr(self.hrow_id), _ptr(self.hrow_segptr), _ptr(self.hseg_hrow),
-                                _ptr(self.hseg_order), _ptr(self.hrow_grpptr), self.n_hgroups, int(self.col.numel()))
+                                _ptr(self.hseg_order), _ptr(self.hrow_grpptr), self.n_hgroups, int(self.col.numel()),
+                                _ptr(self.hitem))
 
     def schedule_for_l2(self, row_bytes: int, window_bytes: int = L2_WINDOW_BYTES):
         """Order the heavy segments by the window of the gathered table they read (rows are column-sorted), so
@@ -223,9 +237,10 @@ def csr_build(src: torch.Tensor, dst: torch.Tensor, n_src: int, n_dst: int, tran
 
 
 def spmm(csr: Csr, x: torch.Tensor, y: torch.Tensor, h: int, *, ew=None, wperm=None, ew2=None, rowsum2=None,
-         bins: int = 1, beta: float = 0.0, bias=None, relu: bool = False):
-    """y[i,:h] = act(beta*y[i,:h] + bias + sum_j w_j x[col_j,:h]).  x / y are 2-D views with row strides."""
-    _need_cuda(x, y, ew, wperm, ew2, rowsum2, bias)
+         bins: int = 1, beta: float = 0.0, bias=None, relu: bool = False, dot_w=None, dot_out=None):
+    """y[i,:h] = act(beta*y[i,:h] + bias + sum_j w_j x[col_j,:h]).  x / y are 2-D views with row strides.
+    dot_w [h] / dot_out [n_rows]: also dot_out[i] = <y[i,:h], dot_w> of the finished row."""
+    _need_cuda(x, y, ew, wperm, ew2, rowsum2, bias, dot_w, dot_out)
     _f32c(x, "spmm x"); _f32c(y, "spmm y")
     if csr.n_rows == 0:
         return y
@@ -238,6 +253,8 @@ def spmm(csr: Csr, x: torch.Tensor, y: torch.Tensor, h: int, *, ew=None, wperm=N
             y[:, :h].clamp_(min=0)
         if rowsum2 is not None:
             rowsum2.zero_()
+        if dot_w is not None:
+            rowdot(y, dot_w, dot_out.view(-1, 1), h, 1, 0)
         return y
     scratch, nbytes = csr.scratch(h)
     global launches
@@ -245,8 +262,8 @@ def spmm(csr: Csr, x: torch.Tensor, y: torch.Tensor, h: int, *, ew=None, wperm=N
     if _prof is not None:
         _prof.begin("spmm", csr, h, beta)
     _check(get_lib().kgb_spmm(C.byref(csr.struct), _ptr(ew), _ptr(wperm), _ptr(ew2), _ptr(rowsum2), bins, _ptr(x),
-                              x.stride(0), _ptr(y), y.stride(0), h, beta, _ptr(bias), int(relu), _ptr(scratch),
-                              nbytes, _stream()), "kgb_spmm")
+                              x.stride(0), _ptr(y), y.stride(0), h, beta, _ptr(bias), int(relu), _ptr(dot_w),
+                              _ptr(dot_out), _ptr(scratch), nbytes, _stream()), "kgb_spmm")
     if _prof is not None:
         _prof.end()
     return y
@@ -293,6 +310,31 @@ def relu_bwd(dy: torch.Tensor, y: torch.Tensor, out: Optional[torch.Tensor] = No
     launches += 1
     _check(get_lib().kgb_relu_bwd(_ptr(dy), _ptr(y), _ptr(out), dy.numel(), _stream()), "kgb_relu_bwd")
     return out
+
+
+def relu_bwd_fused(g: torch.Tensor, h: int, *, dy=None, y=None, dp=None, wv=None, scale: float = 1.0, sums=None):
+    """g[i,:h] = scale * (y[i,:h] > 0) * (dy[i,:h] + dp[i] * wv[:h]);  sums[0] = column sums of g,
+    sums[1] = sum_i dp[i] * y[i,:h]  (kgb_relu_bwd_fused)."""
+    _need_cuda(g, dy, y, dp, wv, sums)
+    for t, name in ((g, "g"), (dy, "dy"), (y, "y")):
+        if t is not None:
+            _f32c(t, "relu_bwd_fused " + name)
+    m = g.size(0)
+    lib = get_lib()
+    ws = None
+    if sums is not None:
+        if sums.numel() != 2 * h or not sums.is_contiguous():
+            raise KgbError("relu_bwd_fused: sums must be a contiguous [2, h] tensor")
+        ws = _workspace(lib.kgb_relu_bwd_fused_workspace_bytes(m, h), g.device)
+    if dp is not None and (not dp.is_contiguous() or dp.numel() != m):
+        raise KgbError("relu_bwd_fused: dp must be a contiguous [m] / [m,1] tensor")
+    global launches
+    launches += 1
+    _check(lib.kgb_relu_bwd_fused(_ptr(dy), dy.stride(0) if dy is not None else 0, _ptr(y),
+                                  y.stride(0) if y is not None else 0, _ptr(dp), _ptr(wv), scale, _ptr(g), g.stride(0), m, h,
+                                  _ptr(sums), _ptr(ws), ws.numel() if ws is not None else 0, _stream()),
+           "kgb_relu_bwd_fused")
+    return g
 
 
 def wcolsum(x: torch.Tensor, h: int, out: torch.Tensor, *, w=None, n_slots: int = 1, beta: float = 0.0):

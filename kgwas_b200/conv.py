@@ -169,8 +169,11 @@ class SAGEConv(nn.Module):
         return f"SAGEConv({self.in_channels}, {self.out_channels}, aggr=mean)"
 
 
-def _hetero_sage(convs: Dict[EdgeType, SAGEConv], x_dict, edge_index_dict, aggr: str, relu: bool, shard=None):
-    """Fused multi-relation SAGE layer (all widths equal).  ``shard``: a dist.ShardContext for SNP-sharded runs."""
+def _hetero_sage(convs: Dict[EdgeType, SAGEConv], x_dict, edge_index_dict, aggr: str, relu: bool, shard=None,
+                 head=None):
+    """Fused multi-relation SAGE layer (all widths equal).  ``shard``: a dist.ShardContext for SNP-sharded runs.
+    ``head`` = (node type, weight [1,h]): also return ``out[node type] . weight^T`` ([N,1], computed in the epilogue
+    of the layer's last kernel) under the key ``('head', node type)``."""
     node_types = list(x_dict.keys())
     num_nodes = {t: int(x.size(0)) for t, x in x_dict.items()}
     if shard is not None:
@@ -191,15 +194,21 @@ def _hetero_sage(convs: Dict[EdgeType, SAGEConv], x_dict, edge_index_dict, aggr:
     for T in plan.dst_types:
         a, b = plan.rel_range[T]
         rel_scale[T] = 1.0 if aggr == "sum" else 1.0 / (b - a)
-    meta = _SageLayerCtx(plan, node_types, h, relu, rel_scale, shard.root_range if shard is not None else None)
+    root_range = shard.root_range if shard is not None else None
+    if head is not None and not (relu and head[0] in plan.dst_types and head[0] not in (root_range or {})):
+        head = None
+    meta = _SageLayerCtx(plan, node_types, h, relu, rel_scale, root_range, head[0] if head is not None else None)
     cs = [convs[et] for et in plan.rel_order]
     for c, et in zip(cs, plan.rel_order):
         c.materialize(h, h)
     outs = HeteroSageLayerFn.apply(meta, *[x_dict[t] for t in node_types], *[c.lin_l.weight for c in cs],
-                                   *[c.lin_l.bias for c in cs], *[c.lin_r.weight for c in cs])
+                                   *[c.lin_l.bias for c in cs], *[c.lin_r.weight for c in cs],
+                                   *([head[1]] if head is not None else []))
     out = dict(zip(plan.dst_types, outs))
     if shard is not None:
         out = shard.combine(out, relu)     # sum the partial rows of shared node types across ranks, then ReLU
+    if head is not None:
+        out[("head", head[0])] = outs[-1]
     return out
 
 
@@ -239,13 +248,16 @@ class HeteroConv(nn.Module):
     def conv_dict(self) -> Dict[EdgeType, nn.Module]:
         return {et: self.convs[_key(et)] for et in self._edge_types}
 
-    def forward(self, x_dict, edge_index_dict, *, _fuse_relu: bool = False, **kwargs_dict):
+    def forward(self, x_dict, edge_index_dict, *, _fuse_relu: bool = False, _head=None, **kwargs_dict):
+        """``_fuse_relu`` / ``_head`` are engine-internal (used by HeteroGNN): apply the ReLU of kgwas/model.py:75 in
+        the layer's last kernel; ``_head=(node_type, weight[1,h])`` additionally asks for ``relu(out[node_type]) .
+        weight^T`` under the key ``('head', node_type)`` when the fused SAGE path can provide it (absent otherwise)."""
         convs = {et: c for et, c in self.conv_dict().items() if et in edge_index_dict}
         kinds = {type(c) for c in convs.values()}
         widths = {int(x.size(-1)) for x in x_dict.values()}
         fusable = self.aggr in ("sum", "mean") and len(widths) == 1 and not kwargs_dict
         if fusable and kinds == {SAGEConv}:
-            return _hetero_sage(convs, x_dict, edge_index_dict, self.aggr, _fuse_relu, self.shard)
+            return _hetero_sage(convs, x_dict, edge_index_dict, self.aggr, _fuse_relu, self.shard, _head)
         if self.shard is not None:
             raise NotImplementedError("SNP-sharded multi-GPU execution is implemented for the hetero-SAGE layer "
                                       "(BASELINE config 4); GAT needs cross-rank softmax statistics (DESIGN.md)")

@@ -113,6 +113,17 @@ struct RowVec {
       for (int i = 0; i < N; ++i) v[i] = __ldg(row + lane * N + i);
     }
   }
+  __device__ __forceinline__ void load_stream(const float* row, int lane) {  // touched once: do not keep in L1
+    if constexpr (H % 128 == 0) {
+#pragma unroll
+      for (int c = 0; c < H / 128; ++c) {
+        float4 t = ldg_stream_f4(row + c * 128 + lane * 4);
+        v[4 * c] = t.x; v[4 * c + 1] = t.y; v[4 * c + 2] = t.z; v[4 * c + 3] = t.w;
+      }
+    } else {
+      load(row, lane);
+    }
+  }
   __device__ __forceinline__ void load_plain(const float* row, int lane) {  // coherent load (data written in-kernel)
     if constexpr (H % 128 == 0) {
 #pragma unroll

@@ -54,6 +54,69 @@ k_wcolsum_stage1(const float* __restrict__ x, int64_t ldx, const float* __restri
     }
   }
 }
+// Fused backward of (ReLU -> single-output head) + bias column sums; see kgb_relu_bwd_fused in kgwas_b200.h.
+// Two rows per warp and iteration in flight; part[b][0][:] = column sums of g, part[b][1][:] = sum dp[i] * y[i,:].
+template <int H>
+__global__ void __launch_bounds__(kColsumThreads)
+k_relu_bwd_fused(const float* __restrict__ dy, int64_t lddy, const float* __restrict__ y, int64_t ldy,
+                 const float* __restrict__ dp, const float* __restrict__ wv, float scale, float* __restrict__ g,
+                 int64_t ldg, int64_t M, int64_t rows_per_cta, float* __restrict__ part) {
+  __shared__ float red[kColsumThreads / 32][H];
+  constexpr int NW = kColsumThreads / 32;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta;
+  const int64_t r1 = min(M, r0 + rows_per_cta);
+  RowVec<H> acc_g, acc_w, wvec;
+  acc_g.zero();
+  acc_w.zero();
+  wvec.zero();
+  if (dp) wvec.load(wv, lane);
+  auto load_row = [&](int64_t m, RowVec<H>& d, RowVec<H>& yv, float& p) {
+    d.zero();
+    yv.zero();
+    p = 0.f;
+    if (m < r1) {
+      if (dy) d.load_stream(dy + m * lddy, lane);
+      if (y) yv.load_stream(y + m * ldy, lane);
+      if (dp) p = __ldg(dp + m);
+    }
+  };
+  auto finish_row = [&](int64_t m, RowVec<H>& d, const RowVec<H>& yv, float p) {
+    if (m >= r1) return;
+    if (dp) d.fma(p, wvec);
+#pragma unroll
+    for (int i = 0; i < RowVec<H>::N; ++i) {
+      const bool on = y ? yv.v[i] > 0.f : true;
+      d.v[i] = on ? d.v[i] * scale : 0.f;
+    }
+    d.store(g + m * ldg, lane);
+    acc_g.add(d);
+    if (dp && y) acc_w.fma(p, yv);
+  };
+  for (int64_t m = r0 + warp; m < r1; m += 2 * NW) {
+    RowVec<H> d0, y0, d1, y1;
+    float p0, p1;
+    load_row(m, d0, y0, p0);
+    load_row(m + NW, d1, y1, p1);
+    finish_row(m, d0, y0, p0);
+    finish_row(m + NW, d1, y1, p1);
+  }
+  if (!part) return;
+  // fold the 8 warps in warp order (fixed => deterministic)
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    __syncthreads();
+    (r == 0 ? acc_g : acc_w).store(&red[warp][0], lane);
+    __syncthreads();
+    for (int c = threadIdx.x; c < H; c += kColsumThreads) {
+      float s = 0.f;
+#pragma unroll
+      for (int q = 0; q < NW; ++q) s += red[q][c];
+      part[((int64_t)blockIdx.x * 2 + r) * H + c] = s;
+    }
+  }
+}
+
 // stage 2: out[i] = beta*out[i] + sum_b part[b][i].  One warp per output element: lanes stride over the chunks
 // (fixed lane <-> chunk mapping, fixed shuffle tree => deterministic), 8 outputs per CTA.
 __global__ void k_wcolsum_stage2(const float* __restrict__ part, int n_ctas, int RH, float* __restrict__ out, float beta) {
@@ -142,6 +205,41 @@ extern "C" int kgb_relu_bwd(const float* dy, const float* y, float* g, int64_t n
   if (ctas < 1) ctas = 1;
   k_relu_bwd<<<(unsigned)ctas, 256, 0, (cudaStream_t)stream_>>>(dy, y, g, n);
   KGB_LAUNCH_OK();
+  return KGB_OK;
+}
+
+extern "C" size_t kgb_relu_bwd_fused_workspace_bytes(int64_t m, int32_t h) {
+  return (size_t)colsum_ctas(m) * 2 * h * sizeof(float) + 256;
+}
+
+extern "C" int kgb_relu_bwd_fused(const float* dy, int64_t lddy, const float* y, int64_t ldy, const float* dp,
+                                  const float* wv, float scale, float* g, int64_t ldg, int64_t m, int32_t h,
+                                  float* sums, void* workspace, size_t workspace_bytes, kgb_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (m == 0) {
+    if (sums) KGB_CUDA_OK(cudaMemsetAsync(sums, 0, (size_t)2 * h * sizeof(float), stream));
+    return KGB_OK;
+  }
+  KGB_REQUIRE(g && m > 0 && (dy || dp), "relu_bwd_fused: bad argument");
+  KGB_REQUIRE((dp == nullptr) == (wv == nullptr), "relu_bwd_fused: dp and wv go together");
+  KGB_REQUIRE(aligned16(g) && ldg % 4 == 0 && (!dy || (aligned16(dy) && lddy % 4 == 0)) &&
+                  (!y || (aligned16(y) && ldy % 4 == 0)) && (!wv || aligned16(wv)),
+              "relu_bwd_fused: pointers must be 16-byte aligned, strides multiples of 4");
+  if (sums && (workspace_bytes < kgb_relu_bwd_fused_workspace_bytes(m, h) || !workspace)) {
+    set_error("relu_bwd_fused: workspace too small");
+    return KGB_ERR_WORKSPACE;
+  }
+  const int64_t ctas = colsum_ctas(m);
+  const int64_t rows_per_cta = (m + ctas - 1) / ctas;
+  float* part = sums ? static_cast<float*>(workspace) : nullptr;
+  KGB_DISPATCH_H(h, (k_relu_bwd_fused<H><<<(unsigned)ctas, kColsumThreads, 0, stream>>>(dy, lddy, y, ldy, dp, wv, scale, g,
+                                                                                     ldg, m, rows_per_cta, part)));
+  KGB_LAUNCH_OK();
+  if (sums) {
+    const int RH = 2 * h;
+    k_wcolsum_stage2<<<(RH + 7) / 8, 256, 0, stream>>>(part, (int)ctas, RH, sums, 0.f);
+    KGB_LAUNCH_OK();
+  }
   return KGB_OK;
 }
 

@@ -112,7 +112,11 @@ class HeteroGNN(nn.Module):
         """model.py:62-86 on already-projected ``[N, hidden]`` features: L x (HeteroConv -> ReLU),
         head, slice.  This is the region the edges-aggregated/s metric is defined on."""
         attention_all_layers = []
-        for conv in self.convs:
+        w_lin = self.lin.weight
+        fuse_head = (not return_attention_weights and w_lin.size(0) == 1 and w_lin.is_cuda
+                     and w_lin.dtype == torch.float32)
+        logits_all = None
+        for li, conv in enumerate(self.convs):
             if return_attention_weights:                                   # model.py:65-72
                 keys = list(edge_index_dict.keys())
                 out = conv(x_dict, edge_index_dict,
@@ -122,9 +126,20 @@ class HeteroGNN(nn.Module):
                 x_dict = {i: j[0].relu() for i, j in out.items()}
                 attention_all_layers.append(mean_attention)
             else:
-                x_dict = conv(x_dict, edge_index_dict, _fuse_relu=True)    # model.py:74-75 (ReLU fused)
-        h_snp = x_dict["SNP"][:batch_size]     # rows are independent: slicing before the head is exact
-        out = self.head(h_snp)
+                # model.py:74-75 (ReLU fused); the last layer also evaluates the single-output head in the epilogue
+                # of the kernel that finishes the SNP rows
+                head = ("SNP", w_lin) if fuse_head and li == len(self.convs) - 1 else None
+                x_dict = conv(x_dict, edge_index_dict, _fuse_relu=True, _head=head)
+                logits_all = x_dict.pop(("head", "SNP"), None)
+        h_snp = x_dict["SNP"]
+        if batch_size < h_snp.size(0):         # rows are independent: slicing before the head is exact
+            h_snp = h_snp[:batch_size]
+        if logits_all is not None:
+            out = logits_all[:batch_size] if batch_size < logits_all.size(0) else logits_all
+            if self.lin.bias is not None:
+                out = out + self.lin.bias
+        else:
+            out = self.head(h_snp)
         if return_h:
             return self.ReLU(out), h_snp
         if return_attention_weights:

@@ -60,8 +60,11 @@ class _SageLayerCtx:
     """Static description handed to the autograd Function (not a tensor)."""
 
     def __init__(self, plan: LayerPlan, node_types: List[str], h: int, relu: bool, rel_scale: Dict[str, float],
-                 root_range: Optional[Dict[str, tuple]] = None):
+                 root_range: Optional[Dict[str, tuple]] = None, head_type: Optional[str] = None):
         self.plan, self.node_types, self.h, self.relu, self.rel_scale = plan, node_types, h, relu, rel_scale
+        # single-output head (kgwas/model.py:50,83) fused into this layer: the Function takes the head weight [1,h]
+        # as one more input and returns <relu(out[head_type]), w> as one more output [N,1]
+        self.head_type = head_type
         # SNP-sharded execution (dist.py): for a destination type whose rows are shared by all ranks, this rank
         # adds the root term (and bias) only for rows [lo, hi); the partial outputs are summed across ranks and
         # the ReLU runs after that sum, outside this Function.
@@ -79,6 +82,9 @@ class HeteroSageLayerFn(torch.autograd.Function):
     outputs: one [N_T,h] tensor per destination type in ``plan.dst_types`` order.
     Relations whose destination type receives no gradient get ``None`` (not zeros), exactly like
     autograd in the reference (those parameters are then skipped by Adam, kgwas/kgwas.py:116,151).
+    With ``meta.head_type`` set: one more input (head weight ``[1,h]``) and one more output
+    ``[N_head, 1] = out[head_type] . w^T`` written by the epilogue of the last kernel that touches those rows; its
+    backward is folded into the ReLU-mask / bias-gradient pass (kgb_relu_bwd_fused).
     """
 
     @staticmethod
@@ -89,6 +95,9 @@ class HeteroSageLayerFn(torch.autograd.Function):
         Wl = torch.stack(tensors[nt:nt + nr])
         bl = torch.stack(tensors[nt + nr:nt + 2 * nr])
         Wr = torch.stack(tensors[nt + 2 * nr:nt + 3 * nr])
+        head_T = meta.head_type
+        w_head = tensors[nt + 3 * nr].contiguous() if head_T is not None else None
+        pred = None
         ctx.set_materialize_grads(False)
         x = dict(zip(meta.node_types, [t.contiguous() for t in xs]))
         outs, saved_A = [], {}
@@ -110,6 +119,8 @@ class HeteroSageLayerFn(torch.autograd.Function):
                 else:                      # A = gather-reduce, then out += A . [W_1|..|W_R]^T
                     job_bufs.append((Wl[lo:hi].permute(1, 0, 2).reshape(h, job.R * h), _empty(n_t, job.R * h, Wl)))
             prep[T] = (_empty(n_t, h, Wl), Wr[a:b].sum(0), bias, job_bufs)
+            if T == head_T:
+                pred = _empty(n_t, 1, Wl)
         # ---- phase 2: one kernel chain per destination type; the largest type (SNP) on the main stream, the
         # others on the side stream: their many small launches hide behind the big gather-reduce kernels ------------
         fork = _Fork(Wl.device)
@@ -120,6 +131,8 @@ class HeteroSageLayerFn(torch.autograd.Function):
             out, w_root, bias, job_bufs = prep[T]
             jobs = plan.jobs[T]
             relu_T = meta.fused_relu(T)
+            # the head dot product rides on the last gather-reduce into these rows (else: one rowdot pass below)
+            head_in_spmm = T == head_T and bool(jobs) and jobs[-1].mode == "xf"
             with fork.stream(T != big):
                 # root term first (dense, overwrites), then every job accumulates; the last writer applies the ReLU.
                 # (A gather-reduce that accumulates re-reads one row per warp, which hides latency far better than
@@ -136,17 +149,25 @@ class HeteroSageLayerFn(torch.autograd.Function):
                     w_job, buf = job_bufs[ji]
                     if job.mode == "xf":
                         _lib.gemm(KGB_NT, xs_, w_job, buf, job.n_src, R * h, h, alpha=scale)
-                        _lib.spmm(job.csr, buf.view(job.n_src * R, h), out, h, ew=job.w_mean, beta=1.0, relu=last_relu)
+                        hd = head_in_spmm and ji == len(jobs) - 1
+                        _lib.spmm(job.csr, buf.view(job.n_src * R, h), out, h, ew=job.w_mean, beta=1.0, relu=last_relu,
+                                  dot_w=w_head if hd else None, dot_out=pred if hd else None)
                     else:
                         _lib.spmm(job.csr, xs_, buf.view(n_t * R, h), h, ew=job.w_mean)
                         _lib.gemm(KGB_NT, buf, w_job, out, n_t, h, R * h, alpha=scale, beta=1.0, relu=last_relu)
                         saved_A[(T, ji)] = buf
+                if T == head_T and not head_in_spmm:
+                    _lib.rowdot(out, w_head, pred, h, 1, 0)
             outs.append(out)
         fork.keep.append(prep)
         fork.join()
         ctx.meta = meta
         ctx.saved_A = saved_A
-        ctx.save_for_backward(Wl, Wr, *[x[t] for t in meta.node_types], *outs)
+        ctx.save_for_backward(Wl, Wr, *[x[t] for t in meta.node_types], *outs, *([w_head] if head_T is not None else []))
+        if head_T is not None:
+            if head_T not in plan.dst_types or not meta.fused_relu(head_T):
+                raise _lib.KgbError("fused head needs its node type to be a destination with the ReLU fused")
+            return (*outs, pred)
         return tuple(outs)
 
     @staticmethod
@@ -159,8 +180,12 @@ class HeteroSageLayerFn(torch.autograd.Function):
         x = dict(zip(meta.node_types, saved[2:2 + n_types]))
         outs = dict(zip(plan.dst_types, saved[2 + n_types:]))
         need_x = dict(zip(meta.node_types, ctx.needs_input_grad[1:1 + n_types]))
-        need_p = ctx.needs_input_grad[1 + n_types:]
+        need_p = ctx.needs_input_grad[1 + n_types:1 + n_types + 3 * nr]
         need_w = any(need_p)
+        head_T = meta.head_type
+        w_head = saved[-1] if head_T is not None else None
+        d_pred = d_outs[len(plan.dst_types)] if head_T is not None else None
+        d_w_head = None
 
         dWl = torch.zeros_like(Wl) if need_w else None
         dbl = torch.zeros((Wl.size(0), h), dtype=torch.float32, device=Wl.device) if need_w else None
@@ -181,15 +206,28 @@ class HeteroSageLayerFn(torch.autograd.Function):
         fork = _Fork(Wl.device)
         order = sorted(range(len(plan.dst_types)), key=lambda i: -plan.num_nodes[plan.dst_types[i]])
         for T, d_out in [(plan.dst_types[i], d_outs[i]) for i in order]:
-            if d_out is None:
+            dp = d_pred if T == head_T else None
+            if d_out is None and dp is None:
                 continue
             a, b = plan.rel_range[T]
             scale = meta.rel_scale[T]
             n_t = plan.num_nodes[T]
-            g = _lib.relu_bwd(d_out, outs[T]) if meta.fused_relu(T) else d_out.contiguous()
-            if scale != 1.0:
-                g = g * scale
-            fork.keep.append(g)
+            sums = None
+            if meta.fused_relu(T):
+                # one pass: ReLU mask (+ the head's rank-1 gradient) -> g, bias gradient, head-weight gradient
+                g = _empty(n_t, h, Wl)
+                if need_w or dp is not None:
+                    sums = _empty(2, h, Wl)
+                _lib.relu_bwd_fused(g, h, dy=d_out.contiguous() if d_out is not None else None, y=outs[T],
+                                    dp=dp.contiguous() if dp is not None else None, wv=w_head if dp is not None else None,
+                                    scale=scale, sums=sums)
+                if dp is not None:
+                    d_w_head = sums[1:2]
+            else:
+                g = d_out.contiguous()
+                if scale != 1.0:
+                    g = g * scale
+            fork.keep += [g, sums]
             for i in range(a, b):
                 used[i] = True
             r0, r1 = meta.root_range.get(T, (0, n_t))          # rows whose root term this rank owns
@@ -199,8 +237,11 @@ class HeteroSageLayerFn(torch.autograd.Function):
                 fork.keep += [db, dwr]
                 fork.sync_side_after_main()
                 with fork.stream(True):
-                    _lib.wcolsum(g[r0:r1], h, db)
-                    dbl[a:b] = db
+                    if sums is not None:
+                        dbl[a:b] = sums[0]
+                    else:
+                        _lib.wcolsum(g[r0:r1], h, db)
+                        dbl[a:b] = db
                     _lib.gemm(KGB_TN, g[r0:r1], x[T][r0:r1], dwr, h, h, r1 - r0)
                     dWr[a:b] = dwr
             if need_x[T]:
@@ -215,7 +256,7 @@ class HeteroSageLayerFn(torch.autograd.Function):
                 if job.mode == "xf":
                     dz = _empty(job.n_src, R * h, g)
                     fork.keep.append(dz)
-                    _lib.spmm(job.tcsr, g, dz.view(job.n_src * R, h), h, ew=job.w_mean, wperm=job.t_eperm)
+                    _lib.spmm(job.tcsr, g, dz.view(job.n_src * R, h), h, ew=job.w_mean_t)
                     if need_w:
                         fork.sync_side_after_main()
                         with fork.stream(True):
@@ -238,7 +279,7 @@ class HeteroSageLayerFn(torch.autograd.Function):
                         fork.keep.append(dA)
                         _lib.gemm(KGB_NN, g, wcat_t, dA, n_t, R * h, h)
                         buf, beta = dx_target(S)
-                        _lib.spmm(job.tcsr, dA.view(n_t * R, h), buf, h, ew=job.w_mean, wperm=job.t_eperm, beta=beta)
+                        _lib.spmm(job.tcsr, dA.view(n_t * R, h), buf, h, ew=job.w_mean_t, beta=beta)
         fork.keep.append(ctx.saved_A)
         fork.join()
         ctx.saved_A = None
@@ -252,4 +293,6 @@ class HeteroSageLayerFn(torch.autograd.Function):
         for k, stacked in enumerate((dWl, dbl, dWr)):
             for i in range(nr):
                 grads_p.append(stacked[i] if (used[i] and need_p[k * nr + i]) else None)
+        if head_T is not None:
+            return (None, *grads_x, *grads_p, d_w_head if ctx.needs_input_grad[1 + n_types + 3 * nr] else None)
         return (None, *grads_x, *grads_p)

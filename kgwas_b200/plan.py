@@ -63,6 +63,9 @@ class PairJob:
         w = (1.0 / deg.clamp(min=1).to(torch.float32))[group]    # SAGE mean: 1 / max(in-degree, 1)
         local_deg = torch.bincount(group, minlength=n_dst * R) if DEG_REDUCE is not None else deg
         self.w_mean = w[self.eperm.long()].contiguous()          # CSR slot order
+        # the same weights in transposed-CSR slot order: static for SAGE, so the backward gather-reduce reads them
+        # directly instead of through the t_eperm indirection (one dependent load less per slice)
+        self.w_mean_t = self.w_mean[self.t_eperm.long()].contiguous()
         if self.mode == "xf":
             # slots are (t, k)-sorted; group row pointers over the same slot order
             gp = torch.zeros(n_dst * R + 1, dtype=torch.int64, device=dev)

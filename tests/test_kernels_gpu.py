@@ -186,3 +186,65 @@ def test_elementwise_helpers(cuda):
     w = torch.randn(1000, device=cuda)
     p = torch.randperm(1000, device=cuda).to(torch.int32)
     assert torch.equal(_lib.permute_f32(w, p), w[p.long()])
+
+
+@pytest.mark.parametrize("h", [32, 128, 256])
+def test_spmm_dot_epilogue(cuda, h):
+    """dot_out[i] = <row i just written, dot_w> for ordinary rows, heavy (segmented) rows and empty rows."""
+    from kgwas_b200 import _lib
+    rng = np.random.default_rng(7 + h)
+    torch.manual_seed(h)
+    n_src, n_dst, e = 500, 260, 20000
+    src, dst = _rand_coo(rng, n_src, n_dst, e, hub=True)
+    dst[dst == 9] = 10
+    s, d = torch.from_numpy(src).to(cuda), torch.from_numpy(dst).to(cuda)
+    fwd, eperm, _, _ = _lib.csr_build(s, d, n_src, n_dst, seg_len=64)
+    assert fwd.n_hsegs > 0
+    x = torch.randn(n_src, h, device=cuda)
+    w_csr = torch.rand(e, device=cuda)
+    bias = torch.randn(h, device=cuda)
+    wv = torch.randn(1, h, device=cuda)
+    y0 = torch.randn(n_dst, h, device=cuda)
+    y_plain = _lib.spmm(fwd, x, y0.clone(), h, ew=w_csr, beta=1.0, bias=bias, relu=True)
+    y, dots = y0.clone(), torch.full((n_dst, 1), 3.0, device=cuda)
+    _lib.spmm(fwd, x, y, h, ew=w_csr, beta=1.0, bias=bias, relu=True, dot_w=wv, dot_out=dots)
+    assert torch.equal(y, y_plain)                                 # the epilogue does not change the rows
+    ref = y.double() @ wv.double().T
+    assert torch.allclose(dots.double(), ref, rtol=1e-5, atol=1e-4 * ref.abs().max().item())
+
+
+@pytest.mark.parametrize("h", [32, 128, 256])
+@pytest.mark.parametrize("m", [1, 17, 5003])
+def test_relu_bwd_fused(cuda, h, m):
+    """g = scale * (y > 0) * (dy + dp (x) wv), sums = [colsum(g), sum_i dp_i y_i]: every nullable combination."""
+    from kgwas_b200 import _lib
+    torch.manual_seed(m + h)
+    dy, y = torch.randn(m, h, device=cuda), torch.randn(m, h, device=cuda)
+    dp, wv = torch.randn(m, 1, device=cuda), torch.randn(1, h, device=cuda)
+    for use_dy, use_y, use_dp, scale in [(True, True, False, 1.0), (False, True, True, 1.0), (True, True, True, 0.5),
+                                         (True, False, False, 2.0)]:
+        g = torch.full((m, h), 9.0, device=cuda)
+        sums = torch.full((2, h), 9.0, device=cuda)
+        _lib.relu_bwd_fused(g, h, dy=dy if use_dy else None, y=y if use_y else None, dp=dp if use_dp else None,
+                            wv=wv if use_dp else None, scale=scale, sums=sums)
+        t = torch.zeros(m, h, device=cuda, dtype=torch.float64)
+        if use_dy:
+            t += dy.double()
+        if use_dp:
+            t += dp.double() * wv.double()
+        ref = scale * t * ((y > 0).double() if use_y else 1.0)
+        tol = 1e-5 * max(1.0, ref.abs().max().item())
+        assert torch.allclose(g.double(), ref, rtol=1e-5, atol=tol)
+        assert torch.allclose(sums[0].double(), ref.sum(0), rtol=1e-5, atol=1e-4 * max(1.0, ref.sum(0).abs().max().item()))
+        if use_dp and use_y:
+            ref1 = (dp.double() * y.double()).sum(0)
+            assert torch.allclose(sums[1].double(), ref1, rtol=1e-5, atol=1e-4 * max(1.0, ref1.abs().max().item()))
+        g2 = torch.empty_like(g)
+        _lib.relu_bwd_fused(g2, h, dy=dy if use_dy else None, y=y if use_y else None, dp=dp if use_dp else None,
+                            wv=wv if use_dp else None, scale=scale)      # without the sums
+        assert torch.equal(g, g2)
+    if m > 1:   # pure mask case is bit-exact and strided inputs are honoured
+        wide = torch.randn(m, 2 * h, device=cuda)
+        g = torch.empty(m, h, device=cuda)
+        _lib.relu_bwd_fused(g, h, dy=wide[:, h:], y=y)
+        assert torch.equal(g, wide[:, h:] * (y > 0))
