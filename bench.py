@@ -38,6 +38,7 @@ def parse():
     p.add_argument("--cpu-scale", type=float, default=0.1, help="graph scale of the bounded CPU sample")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--no-cuda-graph", action="store_true", help="drive every step eagerly from Python")
     p.add_argument("--profile-range", action="store_true",
                    help="wrap the timed steps in cudaProfilerStart/Stop (ncu --profile-from-start off)")
     return p.parse_args()
@@ -259,12 +260,28 @@ def ours(args):
         loss = torch.mean(w_d * (pred - y_d) ** 2)                       # kgwas.py:145
         loss.backward()
         if opt is None:
-            opt = torch.optim.Adam(model.parameters(), lr=1e-4, weight_decay=5e-4)
+            opt = torch.optim.Adam(model.parameters(), lr=1e-4, weight_decay=5e-4, capturable=True)
         opt.step()
         return pred, loss
 
     for _ in range(max(args.warmup, 3)):
         step(x_dev)
+    torch.cuda.synchronize()
+
+    # The full-graph step has fixed shapes: capture it once in a CUDA graph (kgwas_b200.graphed) and replay it --
+    # the eager step is bound by the host (~170 launches issued from Python take longer than the kernels run).
+    graphed, graph_note = None, "off (--no-cuda-graph)"
+    if not args.no_cuda_graph:
+        try:
+            from kgwas_b200.graphed import GraphedStep
+            graphed = GraphedStep(step, x_dev, warmup=3)
+            graph_note = "whole step (fwd + bwd + Adam, both scheduler streams) captured once, replayed per step"
+        except Exception as e:                               # noqa: BLE001 -- report and fall back to the eager step
+            graphed, graph_note = None, f"capture failed, eager steps: {type(e).__name__}: {e}"[:300]
+            torch.cuda.synchronize()
+    run_step = (lambda x: graphed(x)) if graphed is not None else step
+    for _ in range(3):
+        run_step(x_dev)
     torch.cuda.synchronize()
 
     # ---- device-resident throughput ("value")
@@ -278,13 +295,15 @@ def ours(args):
         torch.cuda.profiler.start()
     ev0.record()
     for _ in range(args.steps):
-        step(x_dev)
+        run_step(x_dev)
     ev1.record()
     torch.cuda.synchronize()
     if args.profile_range:
         torch.cuda.profiler.stop()
     ms = ev0.elapsed_time(ev1) / args.steps
     launches = _lib.kernel_launch_count() - k0
+    if graphed is not None:                                  # replays do not pass through the library's launch counter
+        launches = graphed.kernels_per_replay * args.steps
     clk = clocks.stop()
 
     # ---- dominant-kernel roofline: CUDA events around every kgb_spmm launch, on the launching stream, in a second
@@ -335,8 +354,11 @@ def ours(args):
             main_stream.wait_event(ready[b])
             if not last:
                 prefetch(i + 1)
-            x = {k: v.detach().requires_grad_() for k, v in bufs[b].items()}
-            pred, loss = step(x)
+            if graphed is not None:                                  # D2D into the graph's static inputs, then replay
+                pred, loss = graphed(bufs[b])
+            else:
+                x = {k: v.detach().requires_grad_() for k, v in bufs[b].items()}
+                pred, loss = step(x)
             consumed[b].record(main_stream)
             out_host.copy_(pred.detach(), non_blocking=True)
             return loss.item()                                           # D2H + sync
@@ -392,6 +414,7 @@ def ours(args):
                           "bytes_per_edge": b_layer / edges_layer, "achieved": step_gbs, "peak": peak,
                           "unit": "GB/s", "frac": step_gbs / peak, "frac_of_8000_spec": step_gbs / 8000.0},
         "clocks": clk, "gpu_launches": launches, "gpu_launches_per_step": launches / args.steps,
+        "cuda_graph": graph_note,
     }
     if e2e:
         line["e2e"] = e2e

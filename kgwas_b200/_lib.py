@@ -239,7 +239,8 @@ def csr_build(src: torch.Tensor, dst: torch.Tensor, n_src: int, n_dst: int, tran
 def spmm(csr: Csr, x: torch.Tensor, y: torch.Tensor, h: int, *, ew=None, wperm=None, ew2=None, rowsum2=None,
          bins: int = 1, beta: float = 0.0, bias=None, relu: bool = False, dot_w=None, dot_out=None):
     """y[i,:h] = act(beta*y[i,:h] + bias + sum_j w_j x[col_j,:h]).  x / y are 2-D views with row strides.
-    dot_w [h] / dot_out [n_rows]: also dot_out[i] = <y[i,:h], dot_w> of the finished row."""
+    dot_w [h] / dot_out [n_rows]: also dot_out[i] = <y[i,:h], dot_w> of the finished row (h % 128 == 0, no ew2 /
+    wperm: the lean kernel's epilogue)."""
     _need_cuda(x, y, ew, wperm, ew2, rowsum2, bias, dot_w, dot_out)
     _f32c(x, "spmm x"); _f32c(y, "spmm y")
     if csr.n_rows == 0:

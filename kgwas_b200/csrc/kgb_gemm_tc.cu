@@ -17,6 +17,7 @@
 // TN (weight gradients: the reduction runs over graph nodes) is split along K over gridDim.z and
 // the partial tiles are folded in slice order by k_splitk_reduce (deterministic).
 #include "kgb_common.cuh"
+#include <stdlib.h>
 
 namespace kgb {
 
@@ -551,7 +552,9 @@ bool gemm_tc_supported(int layout, int64_t m, int64_t n, int64_t k, int64_t lda,
   if (k < 1) return false;
   // tiny problems: the FFMA kernel has less fixed cost than TMEM allocation + pipeline fill
   const double flops = 2.0 * (double)m * (double)n * (double)k;
-  if (flops < 3.0e7) return false;
+  static const char* tenv = getenv("KGB_GEMM_TC_MIN_FLOPS");   // A/B knob for measurements
+  static const double min_flops = tenv ? atof(tenv) : 3.0e7;
+  if (flops < min_flops) return false;
   if (layout == KGB_TN) return true;
   return true;
 }

@@ -1,5 +1,11 @@
 // Segmented gather-reduce: y[i,:] = beta*y[i,:] + sum_j ew[j] * x[col[j],:]  over a CSR.
 //
+// Two kernels behind kgb_spmm:
+//   * lean::k_spmm_lean (kgb_spmm_lean.cuh) -- the SAGE mean / sum aggregation and its backward (no second scalar, no
+//     weight permutation, h % 128 == 0): instruction-lean, software-pipelined; what the benchmark runs;
+//   * k_spmm below -- the generic kernel: any supported width, weights through a slot permutation (transposed CSR of
+//     the GAT backward), a second per-edge scalar summed per row into bins (attention-logit gradients).
+//
 // HBM-bound byte work: one warp owns one destination row (or one fixed-length
 // segment of a heavy row); every gathered source row is one fully coalesced 128-bit-per-lane
 // request (512 B at h=128), index/weight slices are read 32 at a time and broadcast by shuffle,
@@ -32,281 +38,6 @@ struct Sum2 {
   }
 };
 
-// One 32-slot slice of a CSR row held in registers: lane l owns slot base+l (column, weight, optional second scalar).
-struct Chunk {
-  int c;
-  float w, w2;
-};
-template <bool kSum2>
-__device__ __forceinline__ Chunk load_chunk(const int32_t* __restrict__ col, const EdgeW& e, int base, int end, int lane) {
-  Chunk k{0, 0.f, 0.f};
-  if (base + lane < end) {
-    k.c = __ldg(col + base + lane);
-    const int wi = e.wperm ? __ldg(e.wperm + base + lane) : base + lane;
-    k.w = e.ew ? __ldg(e.ew + wi) : 1.f;
-    if (kSum2) k.w2 = __ldg(e.ew2 + wi);
-  }
-  return k;
-}
-
-// acc += sum over slots [start, end) of w * x[col, :].  `first` = the slice at `start` (already loaded, possibly one
-// item earlier: the row loop below prefetches it).  While a slice is being gathered the next one is already in flight.
-// Gathers go out kUnroll at a time; a ragged tail is a PREDICATED full batch (all of its loads in flight together,
-// w = 0 for the padding), never a serial one-by-one loop -- rows here are short (SNP rows: ~10 in-edges), the batch
-// latency is paid once or twice per row, not once per edge.  Summation order = slot order (deterministic).
-template <int H, int kUnroll, bool kSum2>
-__device__ __forceinline__ void gather_accumulate(RowVec<H>& acc, Sum2& sum2, const int32_t* __restrict__ col,
-                                                  const EdgeW& e, const float* __restrict__ x,
-                                                  int64_t ldx, int start, int end, Chunk cur, int lane) {
-  for (int base = start; base < end; base += kWarp) {
-    const int n = min(kWarp, end - base);
-    const Chunk nxt = load_chunk<kSum2>(col, e, base + kWarp, end, lane);
-    if (kSum2) sum2.add(e.bins > 1 ? cur.c % e.bins : 0, cur.w2);
-    for (int j = 0; j < n; j += kUnroll) {
-      RowVec<H> t[kUnroll];
-      float wj[kUnroll];
-#pragma unroll
-      for (int u = 0; u < kUnroll; ++u) {
-        const int cj = __shfl_sync(0xffffffffu, cur.c, (j + u) & 31);
-        const float ww = __shfl_sync(0xffffffffu, cur.w, (j + u) & 31);
-        const bool valid = j + u < n;                  // warp-uniform
-        wj[u] = valid ? ww : 0.f;
-        if (valid) t[u].load(x + (int64_t)cj * ldx, lane); else t[u].zero();
-      }
-#pragma unroll
-      for (int u = 0; u < kUnroll; ++u) acc.fma(wj[u], t[u]);
-    }
-    cur = nxt;
-  }
-}
-
-// What happens to a finished row: y = act(beta*y + bias + acc), and optionally the row's dot product with a fixed
-// vector (the single-output head of kgwas/model.py:50,83 fused into the last writer of the SNP rows).
-struct Epilogue {
-  float beta;
-  const float* bias;
-  int relu;
-  const float* dot_w;  // [H] or NULL
-  float* dot_out;      // [n_rows]
-};
-
-template <int H>
-__device__ __forceinline__ void write_row_with(const RowVec<H>& acc, const RowVec<H>& old, float* __restrict__ yrow,
-                                               int64_t row, const Epilogue& ep, int lane) {
-  RowVec<H> out = acc;
-  if (ep.bias) {
-    RowVec<H> bv;
-    bv.load(ep.bias, lane);
-    out.add(bv);
-  }
-  if (ep.beta != 0.f) {
-#pragma unroll
-    for (int i = 0; i < RowVec<H>::N; ++i) out.v[i] = fmaf(ep.beta, old.v[i], out.v[i]);
-  }
-  if (ep.relu) {
-#pragma unroll
-    for (int i = 0; i < RowVec<H>::N; ++i) out.v[i] = fmaxf(out.v[i], 0.f);
-  }
-  out.store(yrow, lane);
-  if (ep.dot_w) {
-    RowVec<H> wv;
-    wv.load(ep.dot_w, lane);
-    const float d = warp_sum(out.dot(wv));
-    if (lane == 0) ep.dot_out[row] = d;
-  }
-}
-
-template <int H>
-__device__ __forceinline__ void write_row(const RowVec<H>& acc, float* __restrict__ yrow, int64_t row,
-                                          const Epilogue& ep, int lane) {
-  RowVec<H> old;
-  old.zero();
-  if (ep.beta != 0.f) old.load_plain(yrow, lane);
-  write_row_with<H>(acc, old, yrow, row, ep, lane);
-}
-
-struct HeavyBufs {
-  int32_t* ticket;    // [n_hrows]    groups finished per heavy row
-  int32_t* ticket1;   // [n_hgroups]  segments finished per group
-  float* partial;     // [n_hsegs, H]
-  float* gpartial;    // [n_hgroups, H]
-  float* partial2;    // [n_hsegs, bins]
-  float* gpartial2;   // [n_hgroups, bins]
-};
-
-// sum of n consecutive H-wide rows written earlier in this kernel (coherent loads), 8 in flight, index order
-template <int H>
-__device__ __forceinline__ RowVec<H> fold_rows(const float* base, int n, int lane) {
-  RowVec<H> sum;
-  sum.zero();
-  int i = 0;
-  for (; i + 8 <= n; i += 8) {
-    RowVec<H> p[8];
-#pragma unroll
-    for (int u = 0; u < 8; ++u) p[u].load_plain(base + (int64_t)(i + u) * H, lane);
-#pragma unroll
-    for (int u = 0; u < 8; ++u) sum.add(p[u]);
-  }
-  for (; i < n; ++i) {
-    RowVec<H> p;
-    p.load_plain(base + (int64_t)i * H, lane);
-    sum.add(p);
-  }
-  return sum;
-}
-
-// Work items: [0, n_hsegs) heavy segments (long tasks first), then one item per row; a warp walks the items
-// warp0, warp0 + n_warps, ... -- first its heavy segments, then its rows in a software pipeline:
-//   iteration i   : row pointers of row i+2 requested, first index/weight slice of row i+1 requested, the old
-//                   output row of row i requested (beta != 0), THEN the gathers of row i are issued and summed.
-// Every dependent load of a row was therefore issued one full iteration before it is needed; what a row pays is the
-// latency of its gather batches only (a short row used to pay five to seven dependent round trips).
-// UNROLL = gathers in flight per warp and batch.
-template <int H, int UNROLL, bool kSum2, bool kPipe, int kMinBlocks>
-__global__ void __launch_bounds__(kSpmmThreads, (H <= 128 ? kMinBlocks : 2))
-k_spmm(kgb_csr_t g, EdgeW e, const float* __restrict__ x, int64_t ldx, float* __restrict__ y, int64_t ldy, Epilogue ep,
-       float* __restrict__ rowsum2, HeavyBufs hb) {
-  float* __restrict__ partial = hb.partial;
-  float* __restrict__ partial2 = hb.partial2;
-  const int lane = threadIdx.x & 31;
-  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  int64_t item = warp0;
-  // ---------------------------------------------------------------- heavy segments
-  for (; item < g.n_hsegs; item += n_warps) {
-    const int seg = g.hseg_order ? __ldg(g.hseg_order + item) : (int)item;
-    const int hr = __ldg(g.hseg_hrow + seg);
-    const int row = __ldg(g.hrow_id + hr);
-    const int seg0 = __ldg(g.hrow_segptr + hr), seg1 = __ldg(g.hrow_segptr + hr + 1);
-    const int rs = __ldg(g.rowptr + row), re = __ldg(g.rowptr + row + 1);
-    const int start = rs + (seg - seg0) * g.seg_len;
-    const int end = min(re, start + g.seg_len);
-    RowVec<H> acc;
-    acc.zero();
-    Sum2 s2;
-    s2.zero();
-    gather_accumulate<H, UNROLL, kSum2>(acc, s2, g.col, e, x, ldx, start, end, load_chunk<kSum2>(g.col, e, start, end, lane), lane);
-    acc.store(partial + (int64_t)seg * H, lane);
-    if (kSum2) {
-#pragma unroll
-      for (int b = 0; b < KGB_MAX_BINS; ++b) {
-        if (b < e.bins) {
-          const float t2 = warp_sum(s2.v[b]);
-          if (lane == 0) partial2[(int64_t)seg * e.bins + b] = t2;
-        }
-      }
-    }
-    __threadfence();  // publish this partial before taking a ticket
-    // Two-level fold, each level done by the last finisher and always in index order (deterministic):
-    // KGB_FOLD consecutive segments -> one group partial; the row's group partials -> the output row.
-    const int P = seg1 - seg0;
-    const int gi = (seg - seg0) / KGB_FOLD;
-    const int gsz = min(KGB_FOLD, P - gi * KGB_FOLD);
-    const int grp0 = __ldg(g.hrow_grpptr + hr), ngrp = __ldg(g.hrow_grpptr + hr + 1) - grp0;
-    const int gid = grp0 + gi;
-    int t = 0;
-    if (lane == 0) t = atomicAdd(hb.ticket1 + gid, 1);
-    t = __shfl_sync(0xffffffffu, t, 0);
-    if (t != gsz - 1) continue;
-    __threadfence();
-    {
-      RowVec<H> sum = fold_rows<H>(partial + (int64_t)(seg0 + gi * KGB_FOLD) * H, gsz, lane);
-      sum.store(hb.gpartial + (int64_t)gid * H, lane);
-      if (kSum2 && lane < e.bins) {
-        float t2 = 0.f;
-        const float* p2 = partial2 + (int64_t)(seg0 + gi * KGB_FOLD) * e.bins + lane;
-        for (int s = 0; s < gsz; ++s) t2 += __ldcg(p2 + (int64_t)s * e.bins);
-        hb.gpartial2[(int64_t)gid * e.bins + lane] = t2;
-      }
-      if (lane == 0) hb.ticket1[gid] = 0;  // leave the counters clean for the next launch
-    }
-    __threadfence();
-    if (lane == 0) t = atomicAdd(hb.ticket + hr, 1);
-    t = __shfl_sync(0xffffffffu, t, 0);
-    if (t != ngrp - 1) continue;
-    __threadfence();
-    {
-      RowVec<H> sum = fold_rows<H>(hb.gpartial + (int64_t)grp0 * H, ngrp, lane);
-      write_row<H>(sum, y + (int64_t)row * ldy, row, ep, lane);
-      if (kSum2 && lane < e.bins) {
-        float t2 = 0.f;
-        for (int s = 0; s < ngrp; ++s) t2 += __ldcg(hb.gpartial2 + (int64_t)(grp0 + s) * e.bins + lane);
-        rowsum2[(int64_t)row * e.bins + lane] = t2;
-      }
-      if (lane == 0) hb.ticket[hr] = 0;
-    }
-  }
-  // ---------------------------------------------------------------- rows, software-pipelined
-  // row pointers of a row: start < 0 marks "nothing to do" (past the end, or a heavy row handled above)
-  auto row_meta = [&](int64_t r, int& s, int& en) {
-    s = -1;
-    en = -1;
-    if (r < g.n_rows) {
-      s = __ldg(g.rowptr + r);
-      en = __ldg(g.rowptr + r + 1);
-    }
-  };
-  auto skip = [&](int s, int en) { return s < 0 || (g.n_hsegs > 0 && en - s > g.seg_len); };
-  int64_t row = item - g.n_hsegs;
-  if (!kPipe) {  // plain loop (A/B reference for the pipelined one)
-    for (; row < g.n_rows; row += n_warps) {
-      const int start = __ldg(g.rowptr + row), end = __ldg(g.rowptr + row + 1);
-      if (skip(start, end)) continue;
-      RowVec<H> acc;
-      acc.zero();
-      Sum2 s2;
-      s2.zero();
-      gather_accumulate<H, UNROLL, kSum2>(acc, s2, g.col, e, x, ldx, start, end,
-                                          load_chunk<kSum2>(g.col, e, start, end, lane), lane);
-      write_row<H>(acc, y + row * ldy, row, ep, lane);
-      if (kSum2) {
-#pragma unroll
-        for (int b = 0; b < KGB_MAX_BINS; ++b) {
-          if (b < e.bins) {
-            const float t2 = warp_sum(s2.v[b]);
-            if (lane == 0) rowsum2[row * e.bins + b] = t2;
-          }
-        }
-      }
-    }
-    return;
-  }
-  int sA, eA, sB, eB;
-  row_meta(row, sA, eA);
-  row_meta(row + n_warps, sB, eB);
-  Chunk cA = skip(sA, eA) ? Chunk{0, 0.f, 0.f} : load_chunk<kSum2>(g.col, e, sA, eA, lane);
-  for (; row < g.n_rows; row += n_warps) {
-    int sC, eC;
-    row_meta(row + 2 * n_warps, sC, eC);
-    const Chunk cB = skip(sB, eB) ? Chunk{0, 0.f, 0.f} : load_chunk<kSum2>(g.col, e, sB, eB, lane);
-    if (!skip(sA, eA)) {
-      float* __restrict__ yrow = y + row * ldy;
-      RowVec<H> old;
-      old.zero();
-      if (ep.beta != 0.f) old.load_plain(yrow, lane);
-      RowVec<H> acc;
-      acc.zero();
-      Sum2 s2;
-      s2.zero();
-      gather_accumulate<H, UNROLL, kSum2>(acc, s2, g.col, e, x, ldx, sA, eA, cA, lane);
-      write_row_with<H>(acc, old, yrow, row, ep, lane);
-      if (kSum2) {
-#pragma unroll
-        for (int b = 0; b < KGB_MAX_BINS; ++b) {
-          if (b < e.bins) {
-            const float t2 = warp_sum(s2.v[b]);
-            if (lane == 0) rowsum2[row * e.bins + b] = t2;
-          }
-        }
-      }
-    }
-    sA = sB; eA = eB; cA = cB;
-    sB = sC; eB = eC;
-  }
-}
-
-// ---- variant 0: the pre-pipelining kernel, kept for A/B measurements (KGB_SPMM_VARIANT=0) ----
-namespace v0 {
 template <int H, int kUnroll>
 __device__ __forceinline__ void gather_accumulate(RowVec<H>& acc, Sum2& sum2, const int32_t* __restrict__ col,
                                                   const EdgeW& e, const float* __restrict__ x,
@@ -366,11 +97,41 @@ __device__ __forceinline__ void write_row(const RowVec<H>& acc, float* __restric
   out.store(yrow, lane);
 }
 
+struct HeavyBufs {
+  int32_t* ticket;    // [n_hrows]    groups finished per heavy row
+  int32_t* ticket1;   // [n_hgroups]  segments finished per group
+  float* partial;     // [n_hsegs, H]
+  float* gpartial;    // [n_hgroups, H]
+  float* partial2;    // [n_hsegs, bins]
+  float* gpartial2;   // [n_hgroups, bins]
+};
+
+// sum of n consecutive H-wide rows written earlier in this kernel (coherent loads), 8 in flight, index order
+template <int H>
+__device__ __forceinline__ RowVec<H> fold_rows(const float* base, int n, int lane) {
+  RowVec<H> sum;
+  sum.zero();
+  int i = 0;
+  for (; i + 8 <= n; i += 8) {
+    RowVec<H> p[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) p[u].load_plain(base + (int64_t)(i + u) * H, lane);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) sum.add(p[u]);
+  }
+  for (; i < n; ++i) {
+    RowVec<H> p;
+    p.load_plain(base + (int64_t)i * H, lane);
+    sum.add(p);
+  }
+  return sum;
+}
+
 // Work items: [0, n_hsegs) heavy segments (long tasks first), then one item per row.
 // UNROLL = gathers in flight per warp: 8 for long rows / segments (bandwidth), 4 with one more resident CTA per SM
 // for CSRs dominated by short rows (latency: 784 k SNP rows with ~10 in-edges each).
 template <int H, int UNROLL>
-__global__ void __launch_bounds__(kSpmmThreads, (H <= 128 ? 3 : 2) + (UNROLL <= 4 && H <= 128 ? 1 : 0))
+__global__ void __launch_bounds__(kSpmmThreads, H <= 128 ? 3 : 2)
 k_spmm(kgb_csr_t g, EdgeW e, const float* __restrict__ x, int64_t ldx, float* __restrict__ y, int64_t ldy, float beta,
        const float* __restrict__ bias, int relu, float* __restrict__ rowsum2, HeavyBufs hb) {
   float* __restrict__ partial = hb.partial;
@@ -465,8 +226,6 @@ k_spmm(kgb_csr_t g, EdgeW e, const float* __restrict__ x, int64_t ldx, float* __
   }
 }
 
-}  // namespace v0
-
 inline unsigned spmm_grid(int64_t n_items, int h, bool heavy_dominated) {
   // Persistent grid-stride launch: exactly the number of CTAs that are resident at once (3 per SM at h <= 128,
   // 2 above), so that (a) at any moment the resident warps work on one contiguous range of items -- which is what
@@ -514,7 +273,6 @@ extern "C" int kgb_spmm(const kgb_csr_t* csr, const float* ew, const int32_t* wp
   KGB_REQUIRE(!bias || aligned16(bias), "spmm: bias must be 16-byte aligned");
   KGB_REQUIRE((dot_w == nullptr) == (dot_out == nullptr), "spmm: dot_w and dot_out go together");
   KGB_REQUIRE(!dot_w || aligned16(dot_w), "spmm: dot_w must be 16-byte aligned");
-  const Epilogue ep{beta, bias, relu, dot_w, dot_out};
   HeavyBufs hb{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   if (csr->n_hsegs > 0) {
     KGB_REQUIRE(csr->hrow_grpptr && csr->n_hgroups > 0, "spmm: hrow_grpptr / n_hgroups missing");
@@ -534,47 +292,48 @@ extern "C" int kgb_spmm(const kgb_csr_t* csr, const float* ew, const int32_t* wp
   const EdgeW e{ew, wperm, ew2, ew2 ? rowsum2_bins : 1};
   const bool heavy_dominated = csr->n_edges_hint > 0 && 2 * (int64_t)csr->n_hsegs * csr->seg_len > csr->n_edges_hint;
   const unsigned grid = spmm_grid((int64_t)csr->n_hsegs + csr->n_rows, h, heavy_dominated);
-  // A/B switch for measurements (default 5): 0 = pre-pipelining generic kernel, 1 = generic with pipelined rows,
-  // 2..4 = occupancy / pipelining variants of it, 5 = lean kernel (grid policy as before), 6 = lean, always persistent,
-  // 7 = lean with 4 CTAs / SM
-  static const char* venv = getenv("KGB_SPMM_VARIANT_FIXED");
-  const char* vdyn = venv ? venv : getenv("KGB_SPMM_VARIANT");
-  const int variant = vdyn ? atoi(vdyn) : 5;
-  if (variant >= 5 && !ew2 && !wperm && h % 128 == 0 && (csr->n_hsegs == 0 || csr->hitem)) {
+  // KGB_SPMM_VARIANT=0 forces the generic kernel (A/B measurements: profiles/r01_spmm_variants.md)
+  const char* venv = getenv("KGB_SPMM_VARIANT");   // read per call: scratch/bench_spmm.py flips it at run time
+  const bool want_lean = !(venv && atoi(venv) == 0);
+  const bool lean_ok = !ew2 && !wperm && h % 128 == 0 && (csr->n_hsegs == 0 || csr->hitem);
+  if (dot_w && !lean_ok) {
+    set_error("spmm: the dot-product epilogue needs h %% 128 == 0, no ew2 / wperm, and csr.hitem when rows are segmented");
+    return KGB_ERR_UNSUPPORTED;
+  }
+  if (lean_ok && (want_lean || dot_w)) {
     const lean::Epi lep{beta, bias, relu, dot_w, dot_out};
     const lean::Heavy lhb{hb.ticket, hb.ticket1, hb.partial, hb.gpartial};
-    const int64_t resident = (int64_t)kNumSMs * (h <= 128 ? (variant == 7 ? 4 : 3) : 2);
+    const int64_t resident = (int64_t)kNumSMs * (h <= 128 ? 3 : h <= 384 ? 2 : 1);
     unsigned lgrid = grid;
-    if (variant >= 6 && lgrid > resident) lgrid = (unsigned)resident;
-#define KGB_LEAN(NV, W, MB) lean::k_spmm_lean<NV, W, MB><<<lgrid, lean::kThreads, 0, stream>>>(*csr, ew, x, ldx, y, ldy, lep, lhb)
-#define KGB_LEAN_W(NV, MB) do { if (ew) KGB_LEAN(NV, true, MB); else KGB_LEAN(NV, false, MB); } while (0)
-    switch (h) {
-      case 128: if (variant == 7) KGB_LEAN_W(1, 4); else KGB_LEAN_W(1, 3); break;
-      case 256: KGB_LEAN_W(2, 2); break;
-      case 384: KGB_LEAN_W(3, 2); break;
-      default: KGB_LEAN_W(4, 1); break;
+    // Row-dominated CSRs run `waves` x the resident CTA count instead of one persistent wave: CTA slots then turn
+    // over every ~50 us and the high-priority side streams of the layer scheduler get their small kernels in between
+    // (measured: a captured step is 7.35 ms with one wave, 6.83 ms with 8; the kernel alone loses ~3 %).
+    static const char* wenv = getenv("KGB_SPMM_WAVES");
+    const int waves = wenv ? atoi(wenv) : 8;
+    if (!heavy_dominated) {
+      const int64_t all = ((int64_t)csr->n_hsegs + csr->n_rows + 7) / 8;
+      const int64_t cap = resident * (waves > 0 ? waves : 1);
+      lgrid = (unsigned)(all < cap ? all : cap);
     }
-#undef KGB_LEAN_W
+#define KGB_LEAN(NV, MB)                                                                                             \
+  do {                                                                                                               \
+    if (ew) lean::k_spmm_lean<NV, true, MB, 1, true, 8><<<lgrid, lean::kThreads, 0, stream>>>(*csr, ew, x, ldx, y, ldy, lep, lhb);  \
+    else lean::k_spmm_lean<NV, false, MB, 1, true, 8><<<lgrid, lean::kThreads, 0, stream>>>(*csr, ew, x, ldx, y, ldy, lep, lhb);   \
+  } while (0)
+    switch (h) {
+      case 128: KGB_LEAN(1, 3); break;
+      case 256: KGB_LEAN(2, 2); break;
+      case 384: KGB_LEAN(3, 2); break;
+      case 512: KGB_LEAN(4, 1); break;
+      default:
+        set_error("feature width %d unsupported (need 32,64,128,256,384,512)", (int)h);
+        return KGB_ERR_UNSUPPORTED;
+    }
 #undef KGB_LEAN
     KGB_LAUNCH_OK();
     return KGB_OK;
   }
-#define KGB_SPMM_LAUNCH(S2, PIPE, MB)                                                                           \
-  KGB_DISPATCH_H(h, (k_spmm<H, 8, S2, PIPE, MB><<<grid, kSpmmThreads, 0, stream>>>(*csr, e, x, ldx, y, ldy, ep, rowsum2, hb)))
-  if (variant == 0 && !dot_w) {
-    KGB_DISPATCH_H(h, (v0::k_spmm<H, 8><<<grid, kSpmmThreads, 0, stream>>>(*csr, e, x, ldx, y, ldy, beta, bias, relu, rowsum2, hb)));
-  } else if (ew2) {
-    KGB_SPMM_LAUNCH(true, true, 3);
-  } else if (variant == 2) {
-    KGB_SPMM_LAUNCH(false, true, 2);
-  } else if (variant == 3) {
-    KGB_SPMM_LAUNCH(false, false, 3);
-  } else if (variant == 4) {
-    KGB_SPMM_LAUNCH(false, false, 2);
-  } else {
-    KGB_SPMM_LAUNCH(false, true, 3);
-  }
-#undef KGB_SPMM_LAUNCH
+  KGB_DISPATCH_H(h, (k_spmm<H, 8><<<grid, kSpmmThreads, 0, stream>>>(*csr, e, x, ldx, y, ldy, beta, bias, relu, rowsum2, hb)));
   KGB_LAUNCH_OK();
   return KGB_OK;
 }

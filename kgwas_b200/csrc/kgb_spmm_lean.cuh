@@ -79,7 +79,7 @@ __device__ __forceinline__ void batch(AccT<NV>& acc, const char* __restrict__ xl
 
 // acc += sum over n slots starting at `base`; `cur` is the slice at `base` (n > 32: further slices are fetched here,
 // each one while the previous is being gathered)
-template <int NV, bool kHasW>
+template <int NV, bool kHasW, int kB>
 __device__ __forceinline__ void gather(AccT<NV>& acc, const char* __restrict__ xl, uint32_t ldx_bytes,
                                        const int32_t* __restrict__ col, const float* __restrict__ ew, int base, int n,
                                        Slice cur, int lane) {
@@ -88,7 +88,7 @@ __device__ __forceinline__ void gather(AccT<NV>& acc, const char* __restrict__ x
     Slice nxt{0, 1.f};
     if (n > 32) nxt = load_slice<kHasW>(col, ew, base + 32, n - 32, lane);
     int j = 0;
-    for (; j + 8 <= m; j += 8) batch<NV, 8, kHasW>(acc, xl, ldx_bytes, cur, j);
+    for (; j + kB <= m; j += kB) batch<NV, kB, kHasW>(acc, xl, ldx_bytes, cur, j);
     switch (m - j) {
       case 1: batch<NV, 1, kHasW>(acc, xl, ldx_bytes, cur, j); break;
       case 2: batch<NV, 2, kHasW>(acc, xl, ldx_bytes, cur, j); break;
@@ -191,7 +191,11 @@ __device__ __forceinline__ void store_acc(const AccT<NV>& a, float* row, int lan
 
 constexpr int kThreads = 256;
 
-template <int NV, bool kHasW, int kMinBlocks>
+// kDist: how many rows ahead the index/weight slices are requested (1 or 2); kOldEarly: request the old output row
+// (beta != 0) before the gathers instead of after them; kB (<= 8): gathers in flight per batch.  Measured on B200 at
+// h=128 (profiles/r01_spmm_variants.md): (3 CTAs/SM, kDist 1, early, 8) is the fastest -- a second row of prefetch,
+// a late old-row load, 2 or 4 CTAs per SM and 6- or 12-wide batches all lose 10-40 %; only that one is instantiated.
+template <int NV, bool kHasW, int kMinBlocks, int kDist, bool kOldEarly, int kB>
 __global__ void __launch_bounds__(kThreads, kMinBlocks)
 k_spmm_lean(kgb_csr_t g, const float* __restrict__ ew, const float* __restrict__ x, int64_t ldx, float* __restrict__ y,
             int64_t ldy, Epi ep, Heavy hb) {
@@ -220,7 +224,7 @@ k_spmm_lean(kgb_csr_t g, const float* __restrict__ ew, const float* __restrict__
       const int seg = it.z, hr = it.w;
       AccT<NV> acc;
       acc.zero();
-      gather<NV, kHasW>(acc, xl, ldx_bytes, col, ew, it.x, it.y, cur, lane);
+      gather<NV, kHasW, kB>(acc, xl, ldx_bytes, col, ew, it.x, it.y, cur, lane);
       if (more) cur = load_slice<kHasW>(col, ew, nit.x, nit.y, lane);   // next segment's first slice: in flight during the fold
       store_acc<NV>(acc, hb.partial + (int64_t)seg * H, lane);
       __threadfence();  // publish this partial before taking a ticket
@@ -269,53 +273,80 @@ k_spmm_lean(kgb_csr_t g, const float* __restrict__ ew, const float* __restrict__
   if (first >= g.n_rows) return;
   const int cnt = (g.n_rows - 1 - first) / n_warps + 1;
   const int32_t* __restrict__ rowptr = g.rowptr;
+  const int32_t* __restrict__ col_l = col + lane;         // this lane's element of a slice starting at slot 0
+  const float* __restrict__ ew_l = kHasW ? ew + lane : nullptr;
   const bool has_heavy = g.n_hsegs > 0;
+  const int seg_len = g.seg_len;
   // lane l holds (start, edge count) of iteration blk*32 + l; count < 0: nothing to do (heavy row, done above)
   auto block_meta = [&](int i0, int& ms, int& mn) {
     ms = 0;
     mn = -1;
     const int i = i0 + lane;
     if (i < cnt) {
-      const int64_t r = first + (int64_t)i * n_warps;
-      ms = __ldg(rowptr + r);
-      mn = __ldg(rowptr + r + 1) - ms;
-      if (has_heavy && mn > g.seg_len) mn = -1;
+      const int32_t* rp = rowptr + (first + (int64_t)i * n_warps);
+      ms = __ldg(rp);
+      mn = __ldg(rp + 1) - ms;
+      if (has_heavy && mn > seg_len) mn = -1;
     }
   };
+  auto slice_at = [&](int s, int n) {
+    Slice k{0, 1.f};
+    if (lane < n) {
+      k.c = __ldg(col_l + s);
+      if (kHasW) k.w = __ldg(ew_l + s);
+    }
+    return k;
+  };
+  // Pipeline: row pointers two 32-row blocks ahead; index/weight slices TWO rows ahead (they stream from HBM and take
+  // longer than the gathers, which mostly hit L1/L2); the old output row at the top of its own iteration.
   int ms, mn, ms_nx, mn_nx;
   block_meta(0, ms, mn);
   block_meta(32, ms_nx, mn_nx);
-  int s = __shfl_sync(kFull, ms, 0), n = __shfl_sync(kFull, mn, 0);
-  Slice cur = load_slice<kHasW>(col, ew, s, n, lane);
-  for (int i = 0; i < cnt; ++i) {
-    // ---- requests for later iterations first
-    int s1, n1;
-    if ((i & 31) == 31) {            // next row opens the next block: rotate the prefetched block in, request another
+  int s0 = __shfl_sync(kFull, ms, 0), n0 = __shfl_sync(kFull, mn, 0);
+  int s1 = 0, n1 = -1;
+  Slice c0 = slice_at(s0, n0), c1{0, 1.f};
+  if (kDist == 2) {
+    s1 = __shfl_sync(kFull, ms, 1);
+    n1 = __shfl_sync(kFull, mn, 1);
+    c1 = slice_at(s1, n1);
+  }
+  float* __restrict__ yrow = y + (int64_t)first * ldy;
+  const int64_t ystep = (int64_t)n_warps * ldy;
+  int row = first;
+  for (int i = 0; i < cnt; ++i, yrow += ystep, row += n_warps) {
+    // ---- requests for later iterations first: row pointers of row i+kDist (from the lane-held blocks), its slice
+    int sN, nN;
+    const int k = (i + kDist) & 31;
+    if (k < kDist) {                   // that row lives in the next 32-row block
+      sN = __shfl_sync(kFull, ms_nx, k);
+      nN = __shfl_sync(kFull, mn_nx, k);
+    } else {
+      sN = __shfl_sync(kFull, ms, k);
+      nN = __shfl_sync(kFull, mn, k);
+    }
+    if (k == kDist - 1) {              // every row of the old block that was still needed is out: rotate, request another
       ms = ms_nx;
       mn = mn_nx;
-      block_meta(i + 33, ms_nx, mn_nx);
-      s1 = __shfl_sync(kFull, ms, 0);
-      n1 = __shfl_sync(kFull, mn, 0);
-    } else {
-      s1 = __shfl_sync(kFull, ms, (i + 1) & 31);
-      n1 = __shfl_sync(kFull, mn, (i + 1) & 31);
+      block_meta(i + 1 + 32, ms_nx, mn_nx);
     }
-    const Slice nxt = load_slice<kHasW>(col, ew, s1, n1, lane);   // n1 < 0 (or past the end): no loads
-    if (n >= 0) {
-      const int64_t row = first + (int64_t)i * n_warps;
-      float* __restrict__ yrow = y + row * ldy;
+    const Slice cN = slice_at(sN, nN);                            // nN < 0 (or past the end): no loads
+    if (n0 >= 0) {
       float4 old[NV];
 #pragma unroll
       for (int q = 0; q < NV; ++q) old[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (ep.beta != 0.f) load_old<NV>(old, yrow, lane);
+      if (kOldEarly && ep.beta != 0.f) load_old<NV>(old, yrow, lane);
       AccT<NV> acc;
       acc.zero();
-      if (n > 0) gather<NV, kHasW>(acc, xl, ldx_bytes, col, ew, s, n, cur, lane);
+      if (n0 > 0) gather<NV, kHasW, kB>(acc, xl, ldx_bytes, col, ew, s0, n0, c0, lane);
+      if (!kOldEarly && ep.beta != 0.f) load_old<NV>(old, yrow, lane);
       finish_row<NV>(acc, old, yrow, row, ep, lane);
     }
-    s = s1;
-    n = n1;
-    cur = nxt;
+    if (kDist == 2) {
+      s0 = s1; n0 = n1; c0 = c1;
+      s1 = sN; n1 = nN; c1 = cN;
+    } else {
+      s0 = sN; n0 = nN; c0 = cN;
+    }
   }
 }
 

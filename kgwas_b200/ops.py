@@ -8,6 +8,7 @@ gather-reduce per (destination type, source type) pair -- see plan.py.
 """
 from __future__ import annotations
 
+import functools
 from typing import Dict, List, Optional
 
 import torch
@@ -21,39 +22,153 @@ def _empty(rows, cols, like):
     return torch.empty((rows, cols), dtype=torch.float32, device=like.device)
 
 
-MULTI_STREAM = True      # run independent kernel chains of a layer on a side stream (bench.py turns it off while it
-                         # times single kernels for the roofline, so that their durations are not shared)
+MULTI_STREAM = True      # run the small kernels of a layer on a high-priority side stream (bench.py turns it off while
+                         # it times single kernels for the roofline, so that their durations are not shared)
+BIG_ROWS = 100_000       # an operand with at least this many rows (SNP-sized) makes a launch "big"
+BIG_EDGES = 2_000_000    # ... and so does a gather-reduce over at least this many edges
 _SIDE = {}
+_EVENTS: List["torch.cuda.Event"] = []
+TRACE = None             # scratch/trace_step.py sets this to a list: (label, stream name, start event, end event) per launch
 
 
-class _Fork:
-    """Fork / join of one side CUDA stream inside a layer.  Every buffer is allocated on the main stream BEFORE it is
-    used on the side stream and kept alive until ``join`` (the caching allocator ties a block to its allocation
-    stream), so no ``record_stream`` bookkeeping is needed."""
+class _Sched:
+    """Deferred multi-stream launch scheduler of one layer pass.
+
+    A KGWAS layer is a handful of big kernels (everything that touches the 784 k SNP rows or the 8 M SNP<->Gene edges)
+    and several dozen small ones (gene / GO sized GEMMs and gather-reduces, [h,h] parameter-gradient updates).  Run
+    back to back the small ones cost as much wall time as the big ones while using a fraction of the GPU.
+
+    ``run`` only RECORDS a launch (a closure with bound arguments, what it reads, what it writes, big or small, the
+    chain it belongs to).  ``join`` derives the dependency DAG from program order (RAW / WAW / WAR on whole buffers,
+    tracked per storage), then issues the launches in a topological order that puts first whatever a big kernel is
+    (transitively) waiting for: big launches go to the caller's stream back to back, small ones to a few HIGH-PRIORITY
+    side streams (one per chain, round-robin), so that the block scheduler slips their few CTAs in between the waves of
+    whatever big kernel is running; cross-stream edges of the DAG become event waits.  Dependencies are never spelled
+    out by hand and a stream is never blocked behind a launch it does not depend on.
+
+    Every buffer is allocated on the caller's stream BEFORE ``join`` and kept alive until it returns (the caching
+    allocator ties a block to its allocation stream), so no ``record_stream`` bookkeeping is needed.  Ordinary torch ops
+    issued on the caller's stream while the list is being built are complete (in stream order) before any recorded
+    launch starts."""
+
+    N_SMALL = 3
 
     def __init__(self, device):
+        self.device = device
         self.main = torch.cuda.current_stream(device)
-        self.side = None
+        self.ops = []          # (big, fn, read keys, write keys, label, chain)
         self.keep = []
+        self.smalls = []
         if MULTI_STREAM:
             key = (device.index, self.main.cuda_stream)
             if key not in _SIDE:
-                _SIDE[key] = torch.cuda.Stream(device)
-            self.side = _SIDE[key]
-            self.side.wait_stream(self.main)
+                _SIDE[key] = [torch.cuda.Stream(device, priority=-1) for _ in range(self.N_SMALL)]
+            self.smalls = _SIDE[key]
 
-    def stream(self, on_side: bool):
-        return torch.cuda.stream(self.side if (on_side and self.side is not None) else self.main)
+    def run(self, big: bool, fn, reads=(), writes=(), label="", chain=None):
+        """Record a launch.  ``fn`` takes no arguments, launches kernels only (no allocation) and must not depend on
+        variables that change after this call (bind them with functools.partial / default arguments)."""
+        self.keep.append((reads, writes, fn))
+        rk = [t.untyped_storage().data_ptr() for t in reads if t is not None]
+        wk = [t.untyped_storage().data_ptr() for t in writes if t is not None]
+        self.ops.append((bool(big), fn, rk, wk, label, chain))
 
-    def sync_side_after_main(self):
-        """everything enqueued on main so far happens-before what the side stream is given next"""
-        if self.side is not None:
-            self.side.wait_stream(self.main)
+    def main_made(self, *ts):
+        """kept for call sites that produce operands with ordinary torch ops on the caller's stream: those are ordered
+        before every recorded launch by construction (see class docstring); only keep the tensors alive."""
+        self.keep.append(ts)
 
     def join(self):
-        if self.side is not None:
-            self.main.wait_stream(self.side)
+        """Issue everything recorded so far; on return the caller's stream is ordered after all of it."""
+        ops, self.ops = self.ops, []
+        n = len(ops)
+        if n == 0:
+            self.keep.clear()
+            return
+        if not self.smalls:                                   # single stream: program order
+            for big, fn, _, _, label, _ in ops:
+                self._launch(fn, self.main, label, True)
+            self.keep.clear()
+            return
+        # ---- dependency DAG from program order
+        preds = [set() for _ in range(n)]
+        last_w, readers = {}, {}
+        for i, (_, _, rk, wk, _, _) in enumerate(ops):
+            for k in rk:
+                if k in last_w:
+                    preds[i].add(last_w[k])
+            for k in wk:
+                if k in last_w:
+                    preds[i].add(last_w[k])
+                preds[i].update(readers.get(k, ()))
+            for k in wk:
+                last_w[k] = i
+                readers[k] = []
+            for k in rk:
+                readers.setdefault(k, []).append(i)
+            preds[i].discard(i)
+        succs = [[] for _ in range(n)]
+        for i in range(n):
+            for p in preds[i]:
+                succs[p].append(i)
+        crit = [ops[i][0] for i in range(n)]                   # big, or feeds a big launch
+        for i in range(n - 1, -1, -1):
+            if not crit[i]:
+                crit[i] = any(crit[j] for j in succs[i])
+        # ---- topological issue order: critical launches as early as their inputs allow, else program order
+        import heapq
+        indeg = [len(preds[i]) for i in range(n)]
+        heap = [((0 if crit[i] else 1), i) for i in range(n) if indeg[i] == 0]
+        heapq.heapify(heap)
+        chains, ev_of, st_of = {}, [None] * n, [None] * n
+        start = _event_from_pool(self, 0)
+        start.record(self.main)
+        for st in self.smalls:
+            st.wait_event(start)
+        n_ev = 1
+        while heap:
+            _, i = heapq.heappop(heap)
+            big, fn, _, _, label, chain = ops[i]
+            if big:
+                st = self.main
+            else:
+                if chain not in chains:
+                    chains[chain] = self.smalls[len(chains) % len(self.smalls)]
+                st = chains[chain]
+            for p in preds[i]:
+                if st_of[p] is not st:
+                    st.wait_event(ev_of[p])
+            self._launch(fn, st, label, big)
+            ev = _event_from_pool(self, n_ev)
+            n_ev += 1
+            ev.record(st)
+            ev_of[i], st_of[i] = ev, st
+            for j in succs[i]:
+                indeg[j] -= 1
+                if indeg[j] == 0:
+                    heapq.heappush(heap, ((0 if crit[j] else 1), j))
+        for st in self.smalls:
+            self.main.wait_stream(st)
         self.keep.clear()
+
+    def _launch(self, fn, st, label, big):
+        if TRACE is not None:
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(st)
+        if st is self.main:
+            fn()
+        else:
+            with torch.cuda.stream(st):
+                fn()
+        if TRACE is not None:
+            b.record(st)
+            TRACE.append((label, "big" if st is self.main else f"small{self.smalls.index(st)}", a, b))
+
+
+def _event_from_pool(_sched, i):
+    while len(_EVENTS) <= i:
+        _EVENTS.append(torch.cuda.Event())
+    return _EVENTS[i]
 
 
 class _SageLayerCtx:
@@ -100,7 +215,7 @@ class HeteroSageLayerFn(torch.autograd.Function):
         pred = None
         ctx.set_materialize_grads(False)
         x = dict(zip(meta.node_types, [t.contiguous() for t in xs]))
-        outs, saved_A = [], {}
+        saved_A = {}
         # ---- phase 1 (main stream): allocate every buffer, do the [h,h]-sized parameter reshuffles -------------
         prep = {}
         for T in plan.dst_types:
@@ -121,46 +236,58 @@ class HeteroSageLayerFn(torch.autograd.Function):
             prep[T] = (_empty(n_t, h, Wl), Wr[a:b].sum(0), bias, job_bufs)
             if T == head_T:
                 pred = _empty(n_t, 1, Wl)
-        # ---- phase 2: one kernel chain per destination type; the largest type (SNP) on the main stream, the
-        # others on the side stream: their many small launches hide behind the big gather-reduce kernels ------------
-        fork = _Fork(Wl.device)
-        big = max(plan.dst_types, key=lambda t: plan.num_nodes[t])
-        for T in plan.dst_types:
+        # ---- phase 2: record every launch with the scheduler (nothing runs yet), then let it issue them: big kernels
+        # back to back on this stream, small chains on high-priority side streams, ordered by the data they touch ----
+        sch = _Sched(Wl.device)
+        P = functools.partial
+        for T in sorted(plan.dst_types, key=lambda t: -plan.num_nodes[t]):
             scale = meta.rel_scale[T]
             n_t = plan.num_nodes[T]
             out, w_root, bias, job_bufs = prep[T]
             jobs = plan.jobs[T]
             relu_T = meta.fused_relu(T)
+            big_T = n_t >= BIG_ROWS
             # the head dot product rides on the last gather-reduce into these rows (else: one rowdot pass below)
-            head_in_spmm = T == head_T and bool(jobs) and jobs[-1].mode == "xf"
-            with fork.stream(T != big):
-                # root term first (dense, overwrites), then every job accumulates; the last writer applies the ReLU.
-                # (A gather-reduce that accumulates re-reads one row per warp, which hides latency far better than
-                # a GEMM epilogue re-reading C.)
-                if T in meta.root_range:
-                    r0, r1 = meta.root_range[T]
+            head_in_spmm = T == head_T and bool(jobs) and jobs[-1].mode == "xf" and h % 128 == 0
+            # root term first (dense, overwrites), then every job accumulates; the last writer applies the ReLU.
+            # (A gather-reduce that accumulates re-reads one row per warp, which hides latency far better than
+            # a GEMM epilogue re-reading C.)
+            if T in meta.root_range:
+                r0, r1 = meta.root_range[T]
+
+                def root(out=out, xr=x[T][r0:r1], w_root=w_root, o=out[r0:r1], m=r1 - r0, scale=scale, bias=bias):
                     out.zero_()
-                    _lib.gemm(KGB_NT, x[T][r0:r1], w_root, out[r0:r1], r1 - r0, h, h, alpha=scale, bias=bias)
+                    _lib.gemm(KGB_NT, xr, w_root, o, m, h, h, alpha=scale, bias=bias)
+                sch.run(big_T, root, (x[T], w_root, bias), (out,), f"fwd root {T}", T)
+            else:
+                sch.run(big_T, P(_lib.gemm, KGB_NT, x[T], w_root, out, n_t, h, h, alpha=scale, bias=bias,
+                                 relu=relu_T and not jobs), (x[T], w_root, bias), (out,), f"fwd root {T}", T)
+            for ji, job in enumerate(jobs):
+                R, xs_ = job.R, x[job.src_type]
+                last_relu = relu_T and ji == len(jobs) - 1
+                w_job, buf = job_bufs[ji]
+                big_e = job.n_edges >= BIG_EDGES
+                if job.mode == "xf":
+                    sch.run(job.n_src >= BIG_ROWS, P(_lib.gemm, KGB_NT, xs_, w_job, buf, job.n_src, R * h, h, alpha=scale),
+                            (xs_, w_job), (buf,), f"fwd Z {job.src_type}->{T}", T)
+                    hd = head_in_spmm and ji == len(jobs) - 1
+                    sch.run(big_T or big_e,
+                            P(_lib.spmm, job.csr, buf.view(job.n_src * R, h), out, h, ew=job.w_mean, beta=1.0,
+                              relu=last_relu, dot_w=w_head if hd else None, dot_out=pred if hd else None),
+                            (buf, out, w_head if hd else None), (out, pred if hd else None),
+                            f"fwd spmm xf {job.src_type}->{T}", T)
                 else:
-                    _lib.gemm(KGB_NT, x[T], w_root, out, n_t, h, h, alpha=scale, bias=bias, relu=relu_T and not jobs)
-                for ji, job in enumerate(jobs):
-                    R, xs_ = job.R, x[job.src_type]
-                    last_relu = relu_T and ji == len(jobs) - 1
-                    w_job, buf = job_bufs[ji]
-                    if job.mode == "xf":
-                        _lib.gemm(KGB_NT, xs_, w_job, buf, job.n_src, R * h, h, alpha=scale)
-                        hd = head_in_spmm and ji == len(jobs) - 1
-                        _lib.spmm(job.csr, buf.view(job.n_src * R, h), out, h, ew=job.w_mean, beta=1.0, relu=last_relu,
-                                  dot_w=w_head if hd else None, dot_out=pred if hd else None)
-                    else:
-                        _lib.spmm(job.csr, xs_, buf.view(n_t * R, h), h, ew=job.w_mean)
-                        _lib.gemm(KGB_NT, buf, w_job, out, n_t, h, R * h, alpha=scale, beta=1.0, relu=last_relu)
-                        saved_A[(T, ji)] = buf
-                if T == head_T and not head_in_spmm:
-                    _lib.rowdot(out, w_head, pred, h, 1, 0)
-            outs.append(out)
-        fork.keep.append(prep)
-        fork.join()
+                    sch.run(big_e or job.n_src >= BIG_ROWS,
+                            P(_lib.spmm, job.csr, xs_, buf.view(n_t * R, h), h, ew=job.w_mean), (xs_,), (buf,),
+                            f"fwd spmm af {job.src_type}->{T}", T)
+                    sch.run(big_T, P(_lib.gemm, KGB_NT, buf, w_job, out, n_t, h, R * h, alpha=scale, beta=1.0,
+                                     relu=last_relu), (buf, w_job, out), (out,), f"fwd gemm af {job.src_type}->{T}", T)
+                    saved_A[(T, ji)] = buf
+            if T == head_T and not head_in_spmm:
+                sch.run(big_T, P(_lib.rowdot, out, w_head, pred, h, 1, 0), (out, w_head), (pred,), "fwd head", T)
+        outs = [prep[T][0] for T in plan.dst_types]
+        sch.keep.append(prep)
+        sch.join()
         ctx.meta = meta
         ctx.saved_A = saved_A
         ctx.save_for_backward(Wl, Wr, *[x[t] for t in meta.node_types], *outs, *([w_head] if head_T is not None else []))
@@ -200,10 +327,11 @@ class HeteroSageLayerFn(torch.autograd.Function):
                 return dx[t], 0.0
             return dx[t], 1.0
 
-        # largest destination type first: its dense d x = g . W_root then is the first (overwriting) writer.
-        # Main stream: the d x chain (ReLU mask, NN GEMMs, transposed gather-reduces).  Side stream: everything that only
-        # produces parameter gradients (column sums, TN split-K GEMMs) -- it reads g / dz / A and writes disjoint slices.
-        fork = _Fork(Wl.device)
+        # Largest destination type first: its dense d x = g . W_root then is the first (overwriting) writer.  Launches
+        # are only recorded here; placement (SNP-sized kernels on this stream, everything else on high-priority side
+        # streams), issue order and cross-stream ordering are the scheduler's.
+        sch = _Sched(Wl.device)
+        P = functools.partial
         order = sorted(range(len(plan.dst_types)), key=lambda i: -plan.num_nodes[plan.dst_types[i]])
         for T, d_out in [(plan.dst_types[i], d_outs[i]) for i in order]:
             dp = d_pred if T == head_T else None
@@ -212,76 +340,89 @@ class HeteroSageLayerFn(torch.autograd.Function):
             a, b = plan.rel_range[T]
             scale = meta.rel_scale[T]
             n_t = plan.num_nodes[T]
+            big_T = n_t >= BIG_ROWS
             sums = None
             if meta.fused_relu(T):
                 # one pass: ReLU mask (+ the head's rank-1 gradient) -> g, bias gradient, head-weight gradient
                 g = _empty(n_t, h, Wl)
                 if need_w or dp is not None:
                     sums = _empty(2, h, Wl)
-                _lib.relu_bwd_fused(g, h, dy=d_out.contiguous() if d_out is not None else None, y=outs[T],
-                                    dp=dp.contiguous() if dp is not None else None, wv=w_head if dp is not None else None,
-                                    scale=scale, sums=sums)
+                dy = d_out.contiguous() if d_out is not None else None
+                dpc = dp.contiguous() if dp is not None else None
+                sch.run(big_T, P(_lib.relu_bwd_fused, g, h, dy=dy, y=outs[T], dp=dpc, wv=w_head if dp is not None else None,
+                                 scale=scale, sums=sums),
+                        (dy, outs[T], dpc, w_head), (g, sums), f"bwd relu {T}", T)
                 if dp is not None:
                     d_w_head = sums[1:2]
             else:
                 g = d_out.contiguous()
                 if scale != 1.0:
                     g = g * scale
-            fork.keep += [g, sums]
+                sch.main_made(g)
             for i in range(a, b):
                 used[i] = True
             r0, r1 = meta.root_range.get(T, (0, n_t))          # rows whose root term this rank owns
             if need_w:
                 db = torch.empty(h, dtype=torch.float32, device=g.device)
                 dwr = _empty(h, h, g)
-                fork.keep += [db, dwr]
-                fork.sync_side_after_main()
-                with fork.stream(True):
+
+                def root_grads(sums=sums, gr=g[r0:r1], db=db, dbl_s=dbl[a:b], dWr_s=dWr[a:b], dwr=dwr):
                     if sums is not None:
-                        dbl[a:b] = sums[0]
+                        dbl_s.copy_(sums[0].expand_as(dbl_s))
                     else:
-                        _lib.wcolsum(g[r0:r1], h, db)
-                        dbl[a:b] = db
-                    _lib.gemm(KGB_TN, g[r0:r1], x[T][r0:r1], dwr, h, h, r1 - r0)
-                    dWr[a:b] = dwr
+                        _lib.wcolsum(gr, h, db)
+                        dbl_s.copy_(db.expand_as(dbl_s))
+                    dWr_s.copy_(dwr.expand_as(dWr_s))
+                sch.run(big_T, P(_lib.gemm, KGB_TN, g[r0:r1], x[T][r0:r1], dwr, h, h, r1 - r0), (g, x[T]), (dwr,),
+                        f"bwd dWr {T}", T)
+                sch.run(big_T and sums is None, root_grads, (g, sums, dwr), (db, dbl, dWr), f"bwd rootgrads {T}", T)
             if need_x[T]:
                 buf, beta = dx_target(T)
-                if (r0, r1) != (0, n_t) and beta == 0.0:
-                    buf.zero_()
-                    beta = 1.0
-                _lib.gemm(KGB_NN, g[r0:r1], Wr[a:b].sum(0), buf[r0:r1], r1 - r0, h, h, beta=beta)
+                w_root = Wr[a:b].sum(0)
+                zero_first = (r0, r1) != (0, n_t) and beta == 0.0
+
+                def root_dx(buf=buf, gr=g[r0:r1], w_root=w_root, o=buf[r0:r1], m=r1 - r0, zero_first=zero_first,
+                            beta=1.0 if zero_first else beta):
+                    if zero_first:
+                        buf.zero_()
+                    _lib.gemm(KGB_NN, gr, w_root, o, m, h, h, beta=beta)
+                sch.run(big_T, root_dx, (g, w_root, buf), (buf,), f"bwd dx root {T}", T)
             for ji, job in enumerate(plan.jobs[T]):
                 lo, hi = job.rel_ids[0], job.rel_ids[-1] + 1
                 R, S = job.R, job.src_type
+                big_S = plan.num_nodes[S] >= BIG_ROWS
+                big_e = job.n_edges >= BIG_EDGES
                 if job.mode == "xf":
                     dz = _empty(job.n_src, R * h, g)
-                    fork.keep.append(dz)
-                    _lib.spmm(job.tcsr, g, dz.view(job.n_src * R, h), h, ew=job.w_mean_t)
+                    sch.run(big_T or big_e, P(_lib.spmm, job.tcsr, g, dz.view(job.n_src * R, h), h, ew=job.w_mean_t),
+                            (g,), (dz,), f"bwd spmm xf {T}->{S}", T)
                     if need_w:
-                        fork.sync_side_after_main()
-                        with fork.stream(True):
-                            _lib.gemm(KGB_TN, dz, x[S], dWl[lo:hi].view(R * h, h), R * h, h, job.n_src)
+                        sch.run(big_S, P(_lib.gemm, KGB_TN, dz, x[S], dWl[lo:hi].view(R * h, h), R * h, h, job.n_src),
+                                (dz, x[S]), (dWl,), f"bwd dWl xf {T}->{S}", T)
                     if need_x[S]:
                         buf, beta = dx_target(S)
-                        _lib.gemm(KGB_NN, dz, Wl[lo:hi].reshape(R * h, h), buf, job.n_src, h, R * h, beta=beta)
+                        w_nn = Wl[lo:hi].reshape(R * h, h)
+                        sch.run(big_S, P(_lib.gemm, KGB_NN, dz, w_nn, buf, job.n_src, h, R * h, beta=beta),
+                                (dz, w_nn, buf), (buf,), f"bwd dx xf {T}->{S}", T)
                 else:
                     A = ctx.saved_A[(T, ji)]
                     if need_w:
                         dwt = _empty(h, R * h, g)                              # [h_out, R*h_in]
-                        fork.keep.append(dwt)
-                        fork.sync_side_after_main()
-                        with fork.stream(True):
+
+                        def af_wgrad(g=g, A=A, dwt=dwt, n_t=n_t, R=R, dst=dWl[lo:hi]):
                             _lib.gemm(KGB_TN, g, A, dwt, h, R * h, n_t)
-                            dWl[lo:hi] = dwt.view(h, R, h).permute(1, 0, 2)
+                            dst.copy_(dwt.view(h, R, h).permute(1, 0, 2))
+                        sch.run(big_T, af_wgrad, (g, A), (dwt, dWl), f"bwd dWl af {T}->{S}", T)
                     if need_x[S]:
                         wcat_t = Wl[lo:hi].permute(1, 0, 2).reshape(h, R * h)
                         dA = _empty(n_t, R * h, g)
-                        fork.keep.append(dA)
-                        _lib.gemm(KGB_NN, g, wcat_t, dA, n_t, R * h, h)
+                        sch.run(big_T, P(_lib.gemm, KGB_NN, g, wcat_t, dA, n_t, R * h, h), (g, wcat_t), (dA,),
+                                f"bwd dA af {T}->{S}", T)
                         buf, beta = dx_target(S)
-                        _lib.spmm(job.tcsr, dA.view(n_t * R, h), buf, h, ew=job.w_mean_t, beta=beta)
-        fork.keep.append(ctx.saved_A)
-        fork.join()
+                        sch.run(big_S or big_e, P(_lib.spmm, job.tcsr, dA.view(n_t * R, h), buf, h, ew=job.w_mean_t, beta=beta),
+                                (dA, buf), (buf,), f"bwd spmm af {T}->{S}", T)
+        sch.keep.append(ctx.saved_A)
+        sch.join()
         ctx.saved_A = None
         grads_x = []
         for t in meta.node_types:

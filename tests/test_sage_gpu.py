@@ -139,3 +139,60 @@ def test_state_dict_roundtrip_and_pyg24_keys(cuda):
     # optimiser really updated lazily-materialised conv weights
     first = m.convs[0].convs["Gene__rev_TSS__SNP"].lin_l.weight
     assert first.grad is not None and opt.state[first]["step"] >= 1
+
+
+def test_graphed_step_matches_eager(cuda):
+    """The CUDA-graph capture of a full-graph training step (kgwas_b200.graphed) replays the same kernels in the same
+    order: after 3 optimiser steps the parameters equal those of 3 eager steps."""
+    import kgwas_b200
+    from kgwas_b200 import make_synth_kg
+    from kgwas_b200.graphed import GraphedStep
+    h = 128
+    data = make_synth_kg(scale=0.004, seed=5, hidden=h)
+    n_snp = data["SNP"].x.size(0)
+    gdata = data.to(cuda)
+    yt = torch.randn(n_snp, device=cuda)
+    w = torch.rand(n_snp, device=cuda, dtype=torch.float64)
+    results = []
+    for use_graph in (False, True):
+        torch.manual_seed(11)
+        model = kgwas_b200.HeteroGNN(data, h, 1, 2, "SAGE", "sum", h, h, h, 1)
+        model = model.to(cuda)
+        x = {k: v.clone().requires_grad_() for k, v in gdata.x_dict.items()}
+        with torch.no_grad():                                    # materialise the lazy weights identically in both runs
+            torch.manual_seed(12)
+            model.forward_from_hidden({k: v.detach() for k, v in x.items()}, gdata.edge_index_dict, 4)
+        opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=5e-4, capturable=True)
+        state0 = {k: v.clone() for k, v in model.state_dict().items()}
+
+        def step(xd):
+            opt.zero_grad(set_to_none=True)
+            for v in xd.values():
+                v.grad = None
+            pred = model.forward_from_hidden(xd, gdata.edge_index_dict, n_snp).reshape(-1)
+            loss = torch.mean(w * (pred - yt) ** 2)
+            loss.backward()
+            opt.step()
+            return pred, loss
+
+        if use_graph:
+            gs = GraphedStep(step, x, warmup=2)
+            # the warm-up and the capture pass moved the parameters / optimiser state: rewind both
+            model.load_state_dict(state0)
+            for st in opt.state.values():
+                for v in st.values():
+                    if torch.is_tensor(v):
+                        v.zero_()
+            assert gs.kernels_per_replay > 20
+            for _ in range(3):
+                pred, loss = gs()
+        else:
+            for _ in range(3):
+                pred, loss = step(x)
+        torch.cuda.synchronize()
+        results.append((pred.detach().clone(), loss.detach().clone(), {k: v.clone() for k, v in model.state_dict().items()}))
+    (p0, l0, s0), (p1, l1, s1) = results
+    assert torch.allclose(p0, p1, rtol=1e-5, atol=1e-6 * p0.abs().max().item())
+    assert torch.allclose(l0, l1, rtol=1e-6)
+    for k in s0:
+        assert torch.allclose(s0[k], s1[k], rtol=1e-5, atol=1e-7), k
