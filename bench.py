@@ -260,7 +260,10 @@ def ours(args):
         loss = torch.mean(w_d * (pred - y_d) ** 2)                       # kgwas.py:145
         loss.backward()
         if opt is None:
-            opt = torch.optim.Adam(model.parameters(), lr=1e-4, weight_decay=5e-4, capturable=True)
+            # kgwas.py:116 Adam(lr, weight_decay); the fused implementation is the one that is both a single kernel per
+            # step and legal inside a CUDA graph (the default foreach path is not capturable, and capturable=True
+            # without fused=True falls back to ~170 per-tensor kernels for the step counters)
+            opt = torch.optim.Adam(model.parameters(), lr=1e-4, weight_decay=5e-4, fused=True, capturable=True)
         opt.step()
         return pred, loss
 
@@ -322,8 +325,24 @@ def ours(args):
     pe1.record()
     torch.cuda.synchronize()
     _lib._prof = None
-    _ops.MULTI_STREAM = True
     ms_serial = pe0.elapsed_time(pe1) / prof_steps
+    serial_note = "eager, host-bound"
+    if graphed is not None:
+        # the eager single-stream step is bound by the host; the denominator of the kernel's share of the step is the
+        # same single-stream step replayed from a CUDA graph (pure device time, kernels back to back)
+        try:
+            g1 = GraphedStep(step, x_dev, warmup=1)
+            torch.cuda.synchronize()
+            pe0.record()
+            for _ in range(prof_steps):
+                g1()
+            pe1.record()
+            torch.cuda.synchronize()
+            ms_serial, serial_note = pe0.elapsed_time(pe1) / prof_steps, "CUDA-graph replay, device-bound"
+            del g1
+        except Exception:                                     # noqa: BLE001
+            torch.cuda.synchronize()
+    _ops.MULTI_STREAM = True
     n_spmm, spmm_bytes, spmm_ms = prof.summary("spmm")
 
     # ---- end to end: host (pinned) features -> H2D -> step -> D2H of logits + loss, every step
@@ -392,6 +411,17 @@ def ours(args):
     step_gbs = L * b_layer / (ms * 1e-3) / 1e9
     spmm_gbs = (spmm_bytes / (spmm_ms * 1e-3) / 1e9) if spmm_ms > 0 else 0.0
 
+    # measured DRAM traffic of the same launches (ncu --set full, dram__bytes_read + dram__bytes_write), per launch like
+    # `achieved`: written by scratch/ncu_traffic.py from the capture committed under profiles/
+    traffic, traffic_src = None, None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_spmm_traffic.json")))
+        if tj.get("hidden") == h and tj.get("backbone") == args.backbone and args.scale == 1.0:
+            traffic = tj["dram_bytes_per_step"] / max(1, n_spmm // prof_steps)
+            traffic_src = tj["source"]
+    except Exception:
+        pass
+
     cpu = None
     if not args.no_cpu_baseline:
         r = run_cpu(args, 2, 1, args.cpu_scale)
@@ -404,12 +434,14 @@ def ours(args):
         "config": workload_config(args, 1),
         "edges_per_step": edges_step, "edges_per_layer": edges_layer, "num_nodes": nodes,
         "edge_counts": {"|".join(k): v for k, v in sizes.items()},
-        "roofline": {"bound": "hbm", "kernel": f"k_spmm<{h}> (segmented gather-reduce, all launches of the timed region)",
-                     "achieved": spmm_gbs, "peak": peak, "unit": "GB/s", "frac": spmm_gbs / peak, "traffic": None,
+        "roofline": {"bound": "hbm", "kernel": f"lean::k_spmm_lean<{h // 128}> (segmented gather-reduce, all kgb_spmm launches of a step)",
+                     "achieved": spmm_gbs, "peak": peak, "unit": "GB/s", "frac": spmm_gbs / peak,
+                     "traffic": traffic, "traffic_source": traffic_src,
                      "peak_source": peak_src, "launches_per_step": n_spmm // prof_steps,
                      "algorithmic_bytes_per_step": spmm_bytes / prof_steps,
                      "avg_launch_ms": spmm_ms / max(1, n_spmm), "kernel_share_of_step": spmm_ms / (ms_serial * prof_steps),
-                     "measured_in": f"{prof_steps} extra timed steps, single stream ({ms_serial:.3f} ms/step)"},
+                     "measured_in": f"{prof_steps} extra eager steps, single stream, CUDA events around every kgb_spmm launch; "
+                                    f"share = their sum / single-stream step ({ms_serial:.3f} ms/step, {serial_note})"},
         "roofline_step": {"formula": "SURVEY.md 8(d) B_layer(h)", "bytes_per_layer": b_layer,
                           "bytes_per_edge": b_layer / edges_layer, "achieved": step_gbs, "peak": peak,
                           "unit": "GB/s", "frac": step_gbs / peak, "frac_of_8000_spec": step_gbs / 8000.0},
