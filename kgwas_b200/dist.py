@@ -17,6 +17,7 @@ from __future__ import annotations
 import contextlib
 import json
 import os
+import sys
 import time
 from typing import Dict, Tuple
 
@@ -189,12 +190,32 @@ def bench_sharded(args, rank: int, world: int, dev, helpers):
         params = [p for p in model.parameters() if not isinstance(p, torch.nn.parameter.UninitializedParameter)]
         all_reduce_gradients(params)
         if opt is None:
-            opt = torch.optim.Adam(model.parameters(), lr=1e-4, weight_decay=5e-4)
+            opt = torch.optim.Adam(model.parameters(), lr=1e-4, weight_decay=5e-4, fused=True, capturable=True)
         opt.step()
         return pred, loss
 
     for _ in range(max(args.warmup, 3)):
         step(x_dev)
+
+    # Same as the single-GPU arm: the step (collectives included -- NCCL operations are legal graph nodes) is captured
+    # once and replayed; every rank must agree, so a capture failure anywhere sends all ranks back to eager steps.
+    graphed, graph_note = None, "off (--no-cuda-graph)"
+    if not getattr(args, "no_cuda_graph", False):
+        ok = torch.ones(1, device=dev)
+        try:
+            from .graphed import GraphedStep
+            graphed = GraphedStep(step, x_dev, warmup=3)
+            graph_note = "whole step (fwd + bwd + all-reduces + Adam) captured once per rank, replayed per step"
+        except Exception as e:                               # noqa: BLE001
+            graphed, graph_note = None, f"capture failed, eager steps: {type(e).__name__}: {e}"[:300]
+            ok.zero_()
+            torch.cuda.synchronize()
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if ok.item() == 0 and graphed is not None:
+            graphed, graph_note = None, "capture failed on another rank, eager steps"
+    run_step = (lambda x: graphed(x)) if graphed is not None else step
+    for _ in range(3):
+        run_step(x_dev)
 
     def timed(fn, steps):
         torch.cuda.synchronize()
@@ -213,15 +234,23 @@ def bench_sharded(args, rank: int, world: int, dev, helpers):
     clocks = helpers["ClockSampler"](dev.index)
     clocks.start()
     k0 = _lib.kernel_launch_count()
-    ms = timed(lambda: step(x_dev), args.steps)
+    ms = timed(lambda: run_step(x_dev), args.steps)
     launches = _lib.kernel_launch_count() - k0
+    if graphed is not None:
+        launches = graphed.kernels_per_replay * args.steps
     clk = clocks.stop()
 
     out_host = torch.empty(n_snp, dtype=torch.float32).pin_memory()
 
     def e2e_step():
-        x = {k: v.to(dev, non_blocking=True).requires_grad_() for k, v in x_host.items()}
-        pred, loss = step(x)
+        if graphed is not None:                              # H2D straight into the graph's static inputs, then replay
+            with torch.no_grad():
+                for k, v in x_host.items():
+                    x_dev[k].copy_(v, non_blocking=True)
+            pred, loss = graphed()
+        else:
+            x = {k: v.to(dev, non_blocking=True).requires_grad_() for k, v in x_host.items()}
+            pred, loss = step(x)
         out_host.copy_(pred.detach(), non_blocking=True)
         return loss.item()
 
@@ -244,11 +273,27 @@ def bench_sharded(args, rank: int, world: int, dev, helpers):
                 "rank0_num_nodes": nodes, "collectives_per_step": "per layer: all-reduce(sum) of the shared node "
                 "types' partial rows forward and of their input gradients backward; one flat all-reduce of the "
                 "parameter gradients", "clocks": clk, "gpu_launches": launches,
-                "gpu_launches_per_step": launches / args.steps}
+                "gpu_launches_per_step": launches / args.steps, "cuda_graph": graph_note}
         if e2e_ms is not None:
             line["e2e"] = {"value": edges_step / (e2e_ms * 1e-3), "unit": "edges/s", "ms_per_step": e2e_ms,
                            "h2d_bytes_per_step": world * sum(v.numel() * 4 for v in x_host.values()),
                            "d2h_bytes_per_step": world * (n_snp * 4 + 8)}
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
+    if graphed is not None:
+        import threading
+        # belt and braces for the teardown problem described below: whatever blocks after the result is out, the
+        # process leaves with status 0 half a minute later
+        t = threading.Timer(30.0, lambda: os._exit(0))
+        t.daemon = True
+        t.start()
     dist.barrier()
+    torch.cuda.synchronize()
+    if graphed is not None:
+        # Measured on 2 x B200 (round 1): after the result line is out, destroy_process_group() blocks for as long as a
+        # CUDA graph that captured this communicator's collectives is alive, and the graph cannot be released in a way
+        # that is ordered with NCCL's own teardown.  Every rank has passed the barrier and drained its device: leave
+        # through a hard exit (exit status 0) instead of tearing the communicator down.
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
     dist.destroy_process_group()
