@@ -28,7 +28,56 @@ BIG_ROWS = 100_000       # an operand with at least this many rows (SNP-sized) m
 BIG_EDGES = 2_000_000    # ... and so does a gather-reduce over at least this many edges
 _SIDE = {}
 _EVENTS: List["torch.cuda.Event"] = []
+ISSUE_ORDER_ALWAYS = False   # tests: run the recorded launches in the scheduler's issue order even on a single stream
 TRACE = None             # scratch/trace_step.py sets this to a list: (label, stream name, start event, end event) per launch
+
+
+def issue_order(ops):
+    """Pure scheduling logic of ``_Sched.join`` (unit-tested on CPU).
+
+    ``ops``: program-ordered list of ``(big, read_keys, write_keys)``.  Returns ``(preds, succs, order)``: the
+    dependency DAG implied by program order -- launch i depends on the last earlier writer of everything it reads or
+    writes (RAW, WAW) and on every earlier reader of what it writes since that writer (WAR) -- and a topological issue
+    order in which "critical" launches (big ones and everything a big one transitively depends on) come as early as
+    their inputs allow, the others in program order."""
+    import heapq
+    n = len(ops)
+    preds = [set() for _ in range(n)]
+    last_w, readers = {}, {}
+    for i, (_, rk, wk) in enumerate(ops):
+        for k in rk:
+            if k in last_w:
+                preds[i].add(last_w[k])
+        for k in wk:
+            if k in last_w:
+                preds[i].add(last_w[k])
+            preds[i].update(readers.get(k, ()))
+        for k in wk:
+            last_w[k] = i
+            readers[k] = []
+        for k in rk:
+            readers.setdefault(k, []).append(i)
+        preds[i].discard(i)
+    succs = [[] for _ in range(n)]
+    for i in range(n):
+        for p in preds[i]:
+            succs[p].append(i)
+    crit = [bool(ops[i][0]) for i in range(n)]                 # big, or feeds a big launch
+    for i in range(n - 1, -1, -1):
+        if not crit[i]:
+            crit[i] = any(crit[j] for j in succs[i])
+    indeg = [len(preds[i]) for i in range(n)]
+    heap = [((0 if crit[i] else 1), i) for i in range(n) if indeg[i] == 0]
+    heapq.heapify(heap)
+    order = []
+    while heap:
+        _, i = heapq.heappop(heap)
+        order.append(i)
+        for j in succs[i]:
+            indeg[j] -= 1
+            if indeg[j] == 0:
+                heapq.heappush(heap, ((0 if crit[j] else 1), j))
+    return preds, succs, order
 
 
 class _Sched:
@@ -55,11 +104,12 @@ class _Sched:
 
     def __init__(self, device):
         self.device = device
-        self.main = torch.cuda.current_stream(device)
+        on_gpu = device.type == "cuda"     # (CPU tensors never reach a kernel: _lib raises; tests stub _lib)
+        self.main = torch.cuda.current_stream(device) if on_gpu else None
         self.ops = []          # (big, fn, read keys, write keys, label, chain)
         self.keep = []
         self.smalls = []
-        if MULTI_STREAM:
+        if MULTI_STREAM and on_gpu:
             key = (device.index, self.main.cuda_stream)
             if key not in _SIDE:
                 _SIDE[key] = [torch.cuda.Stream(device, priority=-1) for _ in range(self.N_SMALL)]
@@ -86,48 +136,19 @@ class _Sched:
             self.keep.clear()
             return
         if not self.smalls:                                   # single stream: program order
-            for big, fn, _, _, label, _ in ops:
-                self._launch(fn, self.main, label, True)
+            seq = issue_order([(o[0], o[2], o[3]) for o in ops])[2] if ISSUE_ORDER_ALWAYS else range(n)
+            for i in seq:
+                self._launch(ops[i][1], self.main, ops[i][4], True)
             self.keep.clear()
             return
-        # ---- dependency DAG from program order
-        preds = [set() for _ in range(n)]
-        last_w, readers = {}, {}
-        for i, (_, _, rk, wk, _, _) in enumerate(ops):
-            for k in rk:
-                if k in last_w:
-                    preds[i].add(last_w[k])
-            for k in wk:
-                if k in last_w:
-                    preds[i].add(last_w[k])
-                preds[i].update(readers.get(k, ()))
-            for k in wk:
-                last_w[k] = i
-                readers[k] = []
-            for k in rk:
-                readers.setdefault(k, []).append(i)
-            preds[i].discard(i)
-        succs = [[] for _ in range(n)]
-        for i in range(n):
-            for p in preds[i]:
-                succs[p].append(i)
-        crit = [ops[i][0] for i in range(n)]                   # big, or feeds a big launch
-        for i in range(n - 1, -1, -1):
-            if not crit[i]:
-                crit[i] = any(crit[j] for j in succs[i])
-        # ---- topological issue order: critical launches as early as their inputs allow, else program order
-        import heapq
-        indeg = [len(preds[i]) for i in range(n)]
-        heap = [((0 if crit[i] else 1), i) for i in range(n) if indeg[i] == 0]
-        heapq.heapify(heap)
+        preds, succs, order = issue_order([(o[0], o[2], o[3]) for o in ops])
         chains, ev_of, st_of = {}, [None] * n, [None] * n
         start = _event_from_pool(self, 0)
         start.record(self.main)
         for st in self.smalls:
             st.wait_event(start)
         n_ev = 1
-        while heap:
-            _, i = heapq.heappop(heap)
+        for i in order:
             big, fn, _, _, label, chain = ops[i]
             if big:
                 st = self.main
@@ -143,15 +164,14 @@ class _Sched:
             n_ev += 1
             ev.record(st)
             ev_of[i], st_of[i] = ev, st
-            for j in succs[i]:
-                indeg[j] -= 1
-                if indeg[j] == 0:
-                    heapq.heappush(heap, ((0 if crit[j] else 1), j))
         for st in self.smalls:
             self.main.wait_stream(st)
         self.keep.clear()
 
     def _launch(self, fn, st, label, big):
+        if st is None:                                        # no CUDA stream (stubbed kernels in the CPU tests)
+            fn()
+            return
         if TRACE is not None:
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record(st)

@@ -1,0 +1,95 @@
+"""CPU: host logic of the fused hetero-SAGE layer (plan.py / ops.py / conv.py / model.py) against the oracle, with the
+CUDA kernels replaced by the plain-torch stand-ins of tests/_cpu_kernels.py.  The GPU suite checks the same thing
+through the real kernels; this one keeps the relation merging, accumulate / ReLU placement, head fusion, gradient
+wiring and the scheduler's reordering covered where no GPU is available."""
+import os
+import sys
+
+import pytest
+import torch
+
+from oracle import kgwas_oracle as O
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import _cpu_kernels  # noqa: E402  (tests/_cpu_kernels.py)
+
+
+def _rel(a, b):
+    return ((a.double() - b.double()).abs().max() / b.double().abs().max().clamp(min=1e-12)).item()
+
+
+def _pair(data, h, aggr, no_relu):
+    import kgwas_b200
+    torch.manual_seed(0)
+    ref = O.HeteroGNN(data, h, 1, 2, "SAGE", aggr, h, h, h, 1, no_relu=no_relu)
+    ref({k: v.clone() for k, v in data.x_dict.items()}, data.edge_index_dict, 4)      # materialise lazy weights
+    ours = kgwas_b200.HeteroGNN(data, h, 1, 2, "SAGE", aggr, h, h, h, 1, no_relu=no_relu)
+    ours.load_state_dict(ref.state_dict())
+    return ref, ours
+
+
+@pytest.mark.parametrize("issue_order", [False, True])
+@pytest.mark.parametrize("h,aggr", [(32, "mean"), (128, "sum")])
+def test_fused_layer_host_logic_matches_oracle(monkeypatch, h, aggr, issue_order):
+    from kgwas_b200 import make_synth_kg, ops
+    _cpu_kernels.install(monkeypatch)
+    monkeypatch.setattr(ops, "ISSUE_ORDER_ALWAYS", issue_order)
+    data = make_synth_kg(scale=0.002, seed=3, hidden=h)
+    ref, ours = _pair(data, h, aggr, no_relu=True)
+    bs = 150
+    w = torch.rand(bs, dtype=torch.float64)
+    yt = torch.randn(bs)
+
+    def run(model):
+        x = {k: v.clone().requires_grad_() for k, v in data.x_dict.items()}
+        out = model(x, data.edge_index_dict, bs).reshape(-1)
+        torch.mean(w * (out - yt) ** 2).backward()
+        return out, x
+
+    out_r, x_r = run(ref)
+    out_o, x_o = run(ours)
+    assert out_o.shape == out_r.shape and _rel(out_o, out_r) < 1e-4
+    p_r, p_o = dict(ref.named_parameters()), dict(ours.named_parameters())
+    assert p_r.keys() == p_o.keys()
+    scale = max(p.grad.abs().max().item() for p in p_r.values() if p.grad is not None)
+    for k in p_r:
+        assert (p_r[k].grad is None) == (p_o[k].grad is None), k          # unused last-layer relations: None, not zeros
+        if p_r[k].grad is not None:
+            assert (p_r[k].grad - p_o[k].grad).abs().max().item() <= 2e-4 * scale, k
+    for t in x_r:
+        if x_r[t].grad is None:
+            assert x_o[t].grad is None or x_o[t].grad.abs().max() == 0
+        else:
+            assert _rel(x_o[t].grad, x_r[t].grad) < 2e-4, t
+
+
+def test_fused_head_epilogue_host_logic(monkeypatch):
+    """conv(..., _head=('SNP', w)): the extra output equals relu(out['SNP']) . w^T and its gradient reaches w, the
+    layer parameters and the inputs exactly as the un-fused head does."""
+    import kgwas_b200
+    from kgwas_b200 import make_synth_kg
+    _cpu_kernels.install(monkeypatch)
+    h = 128
+    data = make_synth_kg(scale=0.002, seed=4, hidden=h)
+    torch.manual_seed(1)
+    model = kgwas_b200.HeteroGNN(data, h, 1, 1, "SAGE", "sum", h, h, h, 1)
+    conv = model.convs[0]
+    w_head = torch.randn(1, h, requires_grad=True)
+    res = {}
+    for fused in (True, False):
+        x = {k: v.clone().requires_grad_() for k, v in data.x_dict.items()}
+        out = conv(x, data.edge_index_dict, _fuse_relu=True, _head=("SNP", w_head) if fused else None)
+        logits = out.pop(("head", "SNP")) if fused else out["SNP"] @ w_head.T
+        assert set(out) == {"SNP", "Gene", "CellularComponent", "BiologicalProcess", "MolecularFunction"}
+        model.zero_grad(set_to_none=True)
+        w_head.grad = None
+        (logits.sum() + 0.5 * out["Gene"].sum()).backward()
+        res[fused] = (logits.detach().clone(), w_head.grad.clone(), x["Gene"].grad.clone(),
+                      {k: (None if p.grad is None else p.grad.clone()) for k, p in model.named_parameters()})
+    assert _rel(res[True][0], res[False][0]) < 1e-5
+    assert _rel(res[True][1], res[False][1]) < 1e-5
+    assert _rel(res[True][2], res[False][2]) < 1e-5
+    for k, g in res[False][3].items():
+        assert (g is None) == (res[True][3][k] is None), k
+        if g is not None and g.abs().max() > 0:
+            assert _rel(res[True][3][k], g) < 1e-4, k

@@ -1,0 +1,58 @@
+"""CPU: the launch scheduler's pure logic (kgwas_b200.ops.issue_order) -- the dependency DAG derived from program order
+and the critical-first topological issue order that ``_Sched.join`` turns into stream placement and event waits."""
+import random
+
+from kgwas_b200.ops import issue_order
+
+
+def _simulate(ops, order):
+    """Run the launches in ``order``; each one hashes the current contents of what it reads (and of what it writes:
+    accumulating kernels) into what it writes.  Any legal reordering must end in the same buffer contents."""
+    state = {}
+    for i in order:
+        _, rk, wk = ops[i]
+        seen = tuple(state.get(k, 0) for k in list(rk) + list(wk))
+        for k in wk:
+            state[k] = hash((i, k, seen))
+    return state
+
+
+def test_issue_order_is_a_legal_reordering():
+    rng = random.Random(7)
+    for trial in range(200):
+        n_buf = rng.randint(2, 9)
+        ops = []
+        for _ in range(rng.randint(1, 40)):
+            rk = rng.sample(range(n_buf), rng.randint(0, min(3, n_buf)))
+            wk = rng.sample(range(n_buf), rng.randint(1, min(2, n_buf)))
+            ops.append((rng.random() < 0.3, rk, wk))
+        preds, succs, order = issue_order(ops)
+        assert sorted(order) == list(range(len(ops)))
+        pos = {i: p for p, i in enumerate(order)}
+        for i, ps in enumerate(preds):
+            assert all(p < i for p in ps)                      # the DAG follows program order
+            assert all(pos[p] < pos[i] for p in ps)            # and the issue order respects it
+        for i, ss in enumerate(succs):
+            assert all(i in preds[j] for j in ss)
+        assert _simulate(ops, order) == _simulate(ops, range(len(ops))), trial
+
+
+def test_hazards():
+    # 0 writes A; 1 reads A (RAW on 0); 2 writes A (WAW on 0, WAR on 1); 3 reads B only (independent)
+    ops = [(False, [], ["A"]), (False, ["A"], ["C"]), (False, [], ["A"]), (False, ["B"], ["D"])]
+    preds, _, order = issue_order(ops)
+    assert preds[0] == set() and preds[1] == {0} and preds[2] == {0, 1} and preds[3] == set()
+    assert order == [0, 1, 2, 3]                               # nothing critical: program order
+
+
+def test_critical_launches_go_first():
+    # program order: three independent small launches, then a small one (3) that feeds the big one (4)
+    ops = [(False, ["x"], ["a"]), (False, ["x"], ["b"]), (False, ["x"], ["c"]), (False, ["x"], ["z"]), (True, ["z"], ["out"])]
+    _, _, order = issue_order(ops)
+    assert order[:2] == [3, 4]                                 # the big kernel's producer, then the big kernel
+    assert order[2:] == [0, 1, 2]                              # the rest keeps program order
+    # a small launch that WAITS for a big result must not hold up independent small launches queued after it
+    ops = [(True, ["x"], ["big"]), (False, ["big"], ["y"]), (False, ["x"], ["a"]), (False, ["a"], ["b"])]
+    preds, _, order = issue_order(ops)
+    assert preds[1] == {0} and preds[2] == set()
+    assert order[0] == 0 and sorted(order) == [0, 1, 2, 3]
