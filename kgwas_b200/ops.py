@@ -15,7 +15,7 @@ import torch
 
 from . import _lib
 from ._lib import KGB_NN, KGB_NT, KGB_TN
-from .plan import LayerPlan
+from .plan import BIG_EDGES, BIG_ROWS, LayerPlan
 
 
 def _empty(rows, cols, like):
@@ -24,8 +24,6 @@ def _empty(rows, cols, like):
 
 MULTI_STREAM = True      # run the small kernels of a layer on a high-priority side stream (bench.py turns it off while
                          # it times single kernels for the roofline, so that their durations are not shared)
-BIG_ROWS = 100_000       # an operand with at least this many rows (SNP-sized) makes a launch "big"
-BIG_EDGES = 2_000_000    # ... and so does a gather-reduce over at least this many edges
 _SIDE = {}
 _EVENTS: List["torch.cuda.Event"] = []
 ISSUE_ORDER_ALWAYS = False   # tests: run the recorded launches in the scheduler's issue order even on a single stream
@@ -38,8 +36,10 @@ def issue_order(ops):
     ``ops``: program-ordered list of ``(big, read_keys, write_keys)``.  Returns ``(preds, succs, order)``: the
     dependency DAG implied by program order -- launch i depends on the last earlier writer of everything it reads or
     writes (RAW, WAW) and on every earlier reader of what it writes since that writer (WAR) -- and a topological issue
-    order in which "critical" launches (big ones and everything a big one transitively depends on) come as early as
-    their inputs allow, the others in program order."""
+    order with three classes: "critical" launches (big ones and everything a big one transitively depends on) as early as
+    their inputs allow; then the launches that do not depend on any big launch; "late" ones (small launches that
+    transitively wait for a big kernel) last -- a side stream is a FIFO, a late launch queued early would hold up
+    everything behind it for the duration of that big kernel.  Ties keep program order."""
     import heapq
     n = len(ops)
     preds = [set() for _ in range(n)]
@@ -66,8 +66,12 @@ def issue_order(ops):
     for i in range(n - 1, -1, -1):
         if not crit[i]:
             crit[i] = any(crit[j] for j in succs[i])
+    late = [False] * n                                         # waits (transitively) for a big launch
+    for i in range(n):
+        late[i] = any(ops[p][0] or late[p] for p in preds[i])
+    cls = [0 if crit[i] else (2 if late[i] else 1) for i in range(n)]
     indeg = [len(preds[i]) for i in range(n)]
-    heap = [((0 if crit[i] else 1), i) for i in range(n) if indeg[i] == 0]
+    heap = [(cls[i], i) for i in range(n) if indeg[i] == 0]
     heapq.heapify(heap)
     order = []
     while heap:
@@ -76,7 +80,7 @@ def issue_order(ops):
         for j in succs[i]:
             indeg[j] -= 1
             if indeg[j] == 0:
-                heapq.heappush(heap, ((0 if crit[j] else 1), j))
+                heapq.heappush(heap, (cls[j], j))
     return preds, succs, order
 
 
@@ -353,6 +357,7 @@ class HeteroSageLayerFn(torch.autograd.Function):
         sch = _Sched(Wl.device)
         P = functools.partial
         order = sorted(range(len(plan.dst_types)), key=lambda i: -plan.num_nodes[plan.dst_types[i]])
+        late = []       # recorded after everything else: small consumers of a big gather-reduce (see below)
         for T, d_out in [(plan.dst_types[i], d_outs[i]) for i in order]:
             dp = d_pred if T == head_T else None
             if d_out is None and dp is None:
@@ -416,14 +421,22 @@ class HeteroSageLayerFn(torch.autograd.Function):
                     dz = _empty(job.n_src, R * h, g)
                     sch.run(big_T or big_e, P(_lib.spmm, job.tcsr, g, dz.view(job.n_src * R, h), h, ew=job.w_mean_t),
                             (g,), (dz,), f"bwd spmm xf {T}->{S}", T)
-                    if need_w:
-                        sch.run(big_S, P(_lib.gemm, KGB_TN, dz, x[S], dWl[lo:hi].view(R * h, h), R * h, h, job.n_src),
-                                (dz, x[S]), (dWl,), f"bwd dWl xf {T}->{S}", T)
-                    if need_x[S]:
-                        buf, beta = dx_target(S)
-                        w_nn = Wl[lo:hi].reshape(R * h, h)
-                        sch.run(big_S, P(_lib.gemm, KGB_NN, dz, w_nn, buf, job.n_src, h, R * h, beta=beta),
-                                (dz, w_nn, buf), (buf,), f"bwd dx xf {T}->{S}", T)
+                    def consumers(T=T, S=S, job=job, dz=dz, lo=lo, hi=hi, R=R, big_S=big_S):
+                        if need_w:
+                            sch.run(big_S, P(_lib.gemm, KGB_TN, dz, x[S], dWl[lo:hi].view(R * h, h), R * h, h, job.n_src),
+                                    (dz, x[S]), (dWl,), f"bwd dWl xf {T}->{S}", T)
+                        if need_x[S]:
+                            buf, beta = dx_target(S)
+                            w_nn = Wl[lo:hi].reshape(R * h, h)
+                            sch.run(big_S, P(_lib.gemm, KGB_NN, dz, w_nn, buf, job.n_src, h, R * h, beta=beta),
+                                    (dz, w_nn, buf), (buf,), f"bwd dx xf {T}->{S}", T)
+                    if (big_T or big_e) and not big_S:
+                        # d x[S] accumulates contributions one after the other: a small GEMM that waits for this big
+                        # gather-reduce must be the LAST writer of its buffer, not the first, or every other small
+                        # contribution to d x[S] would be chained behind the big kernel
+                        late.append(consumers)
+                    else:
+                        consumers()
                 else:
                     A = ctx.saved_A[(T, ji)]
                     if need_w:
@@ -441,6 +454,8 @@ class HeteroSageLayerFn(torch.autograd.Function):
                         buf, beta = dx_target(S)
                         sch.run(big_S or big_e, P(_lib.spmm, job.tcsr, dA.view(n_t * R, h), buf, h, ew=job.w_mean_t, beta=beta),
                                 (dA, buf), (buf,), f"bwd spmm af {T}->{S}", T)
+        for rec in late:
+            rec()
         sch.keep.append(ctx.saved_A)
         sch.join()
         ctx.saved_A = None

@@ -27,6 +27,8 @@ from . import _lib
 
 EdgeType = Tuple[str, str, str]
 MAX_SLOTS = 8      # KGB_MAX_BINS of the C ABI
+BIG_ROWS = 100_000       # an operand with at least this many rows (SNP-sized) makes a launch "big" (ops._Sched)
+BIG_EDGES = 2_000_000    # ... and so does a gather-reduce over at least this many edges
 DEG_REDUCE = None  # set by kgwas_b200.dist while a sharded plan is built (all-reduce of the group degrees)
 
 
@@ -133,6 +135,10 @@ class LayerPlan:
             n = sum(j.R for j in self.jobs[T])
             self.rel_range[T] = (pos, pos + n)
             pos += n
+            # Jobs accumulate into the destination rows one after the other.  An aggregate-first job over a big edge
+            # set (SNP -> Gene) ends with a small GEMM that has to wait for its big gather-reduce: put such jobs LAST,
+            # so that the small jobs of this destination type are not chained behind a big kernel (ops._Sched).
+            self.jobs[T].sort(key=lambda j: j.mode == "af" and (j.n_edges >= BIG_EDGES or j.n_src >= BIG_ROWS))
         self.n_edges = sum(j.n_edges for js in self.jobs.values() for j in js)
         self._tensors = [edge_index_dict[et] for et in self.edge_types]   # identity anchors for the cache
         self._versions = [t._version for t in self._tensors]
