@@ -124,7 +124,83 @@ def install(monkeypatch):
     """Swap the kernel entry points of kgwas_b200._lib for the stand-ins above (pytest monkeypatch: undone per test)."""
     from kgwas_b200 import _lib, ops, plan
     for name, fn in (("csr_build", csr_build), ("spmm", spmm), ("gemm", gemm), ("relu_bwd", relu_bwd),
-                     ("relu_bwd_fused", relu_bwd_fused), ("wcolsum", wcolsum), ("rowdot", rowdot), ("Csr", FakeCsr)):
+                     ("relu_bwd_fused", relu_bwd_fused), ("wcolsum", wcolsum), ("rowdot", rowdot), ("Csr", FakeCsr)) + _GAT:
         monkeypatch.setattr(_lib, name, fn)
     monkeypatch.setattr(ops, "MULTI_STREAM", False)
     plan.clear_plan_cache()
+
+
+# ---- GAT edge kernels (include/kgwas_b200.h: kgb_gat_alpha / kgb_sddmm / kgb_gat_dsoftmax) ----------------------------
+
+def _groups(groups, n_slots, src_is_node):
+    deg = (groups.rowptr[1:] - groups.rowptr[:-1]).long()
+    g = torch.repeat_interleave(torch.arange(groups.n_rows), deg)
+    col = groups.col.long()
+    return g, (col * n_slots + g % n_slots) if src_is_node else col
+
+
+def _seg_sum(v, g, n):
+    return torch.zeros(n, dtype=v.dtype).index_add_(0, g, v)
+
+
+def gat_alpha(groups, a_src, a_dst, n_slots, src_is_node, alpha, slope, temperature, mode):
+    if groups.n_edges == 0:
+        return alpha
+    g, si = _groups(groups, n_slots, src_is_node)
+    u = a_src.reshape(-1)[si] + a_dst.reshape(-1)[g]
+    z = torch.nn.functional.leaky_relu(u, slope)
+    if mode == 2:
+        alpha.copy_(z)
+    elif mode == 1:
+        alpha.copy_(torch.sigmoid(z / temperature))
+    else:
+        s = z / temperature
+        m = torch.full((groups.n_rows,), float("-inf")).scatter_reduce_(0, g, s, "amax")
+        e = torch.exp(s - m[g])
+        alpha.copy_(e / (_seg_sum(e, g, groups.n_rows) + 1e-16)[g])
+    return alpha
+
+
+def sddmm(csr, xrow, x, h, out):
+    if csr.n_edges == 0:
+        return out
+    deg = (csr.rowptr[1:] - csr.rowptr[:-1]).long()
+    r = torch.repeat_interleave(torch.arange(csr.n_rows), deg)
+    out.copy_((xrow[r, :h] * x[csr.col.long(), :h]).sum(-1))
+    return out
+
+
+def gat_dsoftmax(groups, a_src, a_dst, n_slots, src_is_node, alpha, dalpha, du, da_dst, slope, temperature, mode):
+    if groups.n_rows == 0:
+        return du, da_dst
+    if groups.n_edges == 0:
+        da_dst.zero_()
+        return du, da_dst
+    g, si = _groups(groups, n_slots, src_is_node)
+    u = a_src.reshape(-1)[si] + a_dst.reshape(-1)[g]
+    if mode == 2:
+        dz = dalpha.clone()
+    elif mode == 1:
+        dz = alpha * (1 - alpha) * dalpha / temperature
+    else:
+        dz = alpha * (dalpha - _seg_sum(alpha * dalpha, g, groups.n_rows)[g]) / temperature
+    du.copy_(dz * torch.where(u > 0, torch.ones_like(u), torch.full_like(u, slope)))
+    da_dst.view(-1).copy_(_seg_sum(du, g, groups.n_rows))
+    return du, da_dst
+
+
+def rank_update(a, v, y, h, n_slots, beta):
+    y[:, :h] = a[:, :n_slots] @ v[:n_slots, :h] + (beta * y[:, :h] if beta != 0.0 else 0.0)
+    return y
+
+
+def permute_f32(w, perm, out=None):
+    r = w[perm.long()]
+    if out is not None:
+        out.copy_(r)
+        return out
+    return r
+
+
+_GAT = (("gat_alpha", gat_alpha), ("sddmm", sddmm), ("gat_dsoftmax", gat_dsoftmax), ("rank_update", rank_update),
+        ("permute_f32", permute_f32))

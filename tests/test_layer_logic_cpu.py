@@ -93,3 +93,40 @@ def test_fused_head_epilogue_host_logic(monkeypatch):
         assert (g is None) == (res[True][3][k] is None), k
         if g is not None and g.abs().max() > 0:
             assert _rel(res[True][3][k], g) < 1e-4, k
+
+
+@pytest.mark.parametrize("h,aggr", [(32, "sum"), (64, "mean")])
+def test_fused_gat_layer_host_logic_matches_oracle(monkeypatch, h, aggr):
+    """Same for the hetero-GAT layer (gat.py): folded attention logits, transform-first / aggregate-first jobs,
+    softmax-group bookkeeping, parameter-gradient folding -- against the oracle, kernels stubbed."""
+    import kgwas_b200
+    from kgwas_b200 import make_synth_kg
+    _cpu_kernels.install(monkeypatch)
+    data = make_synth_kg(scale=0.002, seed=5, hidden=h)
+    torch.manual_seed(0)
+    ref = O.HeteroGNN(data, h, 1, 2, "GAT", aggr, h, h, h, 1, no_relu=True)
+    ref({k: v.clone() for k, v in data.x_dict.items()}, data.edge_index_dict, 4)
+    ours = kgwas_b200.HeteroGNN(data, h, 1, 2, "GAT", aggr, h, h, h, 1, no_relu=True)
+    ours.load_state_dict(ref.state_dict())
+    bs = 150
+    w = torch.rand(bs, dtype=torch.float64)
+    yt = torch.randn(bs)
+
+    def run(model):
+        out = model({k: v.clone() for k, v in data.x_dict.items()}, data.edge_index_dict, bs).reshape(-1)
+        torch.mean(w * (out - yt) ** 2).backward()
+        return out
+
+    out_r, out_o = run(ref), run(ours)
+    assert _rel(out_o, out_r) < 1e-4
+    p_r, p_o = dict(ref.named_parameters()), dict(ours.named_parameters())
+    assert p_r.keys() == p_o.keys()
+    lazy = torch.nn.parameter.UninitializedParameter
+    scale = max(p.grad.abs().max().item() for p in p_r.values() if not isinstance(p, lazy) and p.grad is not None)
+    for k in p_r:
+        assert isinstance(p_r[k], lazy) == isinstance(p_o[k], lazy), k
+        if isinstance(p_r[k], lazy):
+            continue
+        assert (p_r[k].grad is None) == (p_o[k].grad is None), k
+        if p_r[k].grad is not None:
+            assert (p_r[k].grad - p_o[k].grad).abs().max().item() <= 1e-3 * scale, k
