@@ -314,6 +314,9 @@ class HeteroSageLayerFn(torch.autograd.Function):
         sch.join()
         ctx.meta = meta
         ctx.saved_A = saved_A
+        # [h,h]-sized derived operands the backward needs again (pre-summed root weights, concatenated job weights):
+        # kept instead of being recomputed by a dozen tiny launches at the head of the backward pass
+        ctx.derived = {T: (prep[T][1], [wb[0] for wb in prep[T][3]]) for T in plan.dst_types}
         ctx.save_for_backward(Wl, Wr, *[x[t] for t in meta.node_types], *outs, *([w_head] if head_T is not None else []))
         if head_T is not None:
             if head_T not in plan.dst_types or not meta.fused_relu(head_T):
@@ -403,7 +406,7 @@ class HeteroSageLayerFn(torch.autograd.Function):
                 sch.run(big_T and sums is None, root_grads, (g, sums, dwr), (db, dbl, dWr), f"bwd rootgrads {T}", T)
             if need_x[T]:
                 buf, beta = dx_target(T)
-                w_root = Wr[a:b].sum(0)
+                w_root = ctx.derived[T][0]                                   # sum of the relations' root weights
                 zero_first = (r0, r1) != (0, n_t) and beta == 0.0
 
                 def root_dx(buf=buf, gr=g[r0:r1], w_root=w_root, o=buf[r0:r1], m=r1 - r0, zero_first=zero_first,
@@ -447,7 +450,7 @@ class HeteroSageLayerFn(torch.autograd.Function):
                             dst.copy_(dwt.view(h, R, h).permute(1, 0, 2))
                         sch.run(big_T, af_wgrad, (g, A), (dwt, dWl), f"bwd dWl af {T}->{S}", T)
                     if need_x[S]:
-                        wcat_t = Wl[lo:hi].permute(1, 0, 2).reshape(h, R * h)
+                        wcat_t = ctx.derived[T][1][ji]                         # [h, R*h] = [W_1 | .. | W_R]
                         dA = _empty(n_t, R * h, g)
                         sch.run(big_T, P(_lib.gemm, KGB_NN, g, wcat_t, dA, n_t, R * h, h), (g, wcat_t), (dA,),
                                 f"bwd dA af {T}->{S}", T)
@@ -459,6 +462,7 @@ class HeteroSageLayerFn(torch.autograd.Function):
         sch.keep.append(ctx.saved_A)
         sch.join()
         ctx.saved_A = None
+        ctx.derived = None
         grads_x = []
         for t in meta.node_types:
             if need_x[t] and dx[t] is None:      # no gradient reached this type: autograd treats None as zero
