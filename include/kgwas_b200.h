@@ -92,6 +92,11 @@ KGB_API int kgb_csr_heavy_fill(const int32_t* rowptr, int32_t n_rows, int32_t se
  * dot_w [h] / dot_out [n_rows] (both or neither): dot_out[i] = <y[i,:], dot_w> of the row just
  * written -- the single-output head `self.lin` applied to the ReLU-ed SNP rows (kgwas/model.py:50,
  * 83-86) without a second pass over the [N_SNP, h] tensor.
+ * Dispatch: ew2 == NULL, wperm == NULL and h % 128 == 0 (every launch of the SAGE path) runs the
+ * instruction-lean, software-pipelined kernel; anything else the generic one.  Results do not
+ * depend on the kernel (same summation order).  Environment knobs for A/B measurements only:
+ * KGB_SPMM_VARIANT=0 forces the generic kernel, KGB_SPMM_WAVES=n sets the CTA waves of
+ * row-dominated launches (default 8).
  * heavy_* come from kgb_csr_heavy_*; pass n_hrows = n_hsegs = 0 when no row exceeds seg_len.
  * scratch: kgb_spmm_scratch_bytes(), zero-initialised ONCE by the caller (the kernel leaves its
  * ticket counters zero again on exit); may be NULL when n_hsegs == 0. */
@@ -108,7 +113,7 @@ typedef struct {
   const int32_t* hseg_order; /* nullable: work item i processes segment hseg_order[i] (L2-window scheduling) */
   const int32_t* hrow_grpptr; /* [n_hrows+1] prefix sum of ceil(segments / KGB_FOLD) per heavy row */
   int32_t n_hgroups;          /* hrow_grpptr[n_hrows] */
-  int64_t n_edges_hint;       /* rowptr[n_rows] if known on the host, else 0: picks the short-row kernel variant */
+  int64_t n_edges_hint;       /* rowptr[n_rows] if known on the host, else 0: grid policy (row- vs segment-dominated) */
   const int32_t* hitem;       /* nullable [n_hsegs][4]: work item i = (first slot, slot count, segment id, heavy-row
                                  slot) in hseg_order order -- everything a warp needs to start a segment in ONE
                                  16-byte load (the lean kernel needs it when n_hsegs > 0) */
