@@ -258,12 +258,12 @@ class HeteroConv(nn.Module):
         fusable = self.aggr in ("sum", "mean") and len(widths) == 1 and not kwargs_dict
         if fusable and kinds == {SAGEConv}:
             return _hetero_sage(convs, x_dict, edge_index_dict, self.aggr, _fuse_relu, self.shard, _head)
-        if self.shard is not None:
-            raise NotImplementedError("SNP-sharded multi-GPU execution is implemented for the hetero-SAGE layer "
-                                      "(BASELINE config 4); GAT needs cross-rank softmax statistics (DESIGN.md)")
         from .gat import GATConv, hetero_gat   # noqa: local import keeps module load light
         if self.aggr in ("sum", "mean") and len(widths) == 1 and kinds == {GATConv}:
-            return hetero_gat(convs, x_dict, edge_index_dict, self.aggr, _fuse_relu, kwargs_dict)
+            return hetero_gat(convs, x_dict, edge_index_dict, self.aggr, _fuse_relu, kwargs_dict, self.shard)
+        if self.shard is not None:
+            raise NotImplementedError("SNP-sharded multi-GPU execution needs the fused hetero-SAGE / hetero-GAT layer "
+                                      "(sum or mean aggregation, one conv kind, equal widths)")
         return self._per_relation(convs, x_dict, edge_index_dict, _fuse_relu, kwargs_dict)
 
     def _per_relation(self, convs, x_dict, edge_index_dict, relu, kwargs_dict):

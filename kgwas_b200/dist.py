@@ -62,6 +62,7 @@ def split_range(n: int, rank: int, world: int) -> Tuple[int, int]:
 class ShardContext:
     def __init__(self, rank: int, world: int, root_range: Dict[str, Tuple[int, int]]):
         self.rank, self.world, self.root_range = rank, world, root_range
+        self.sharded_type = SHARDED_TYPE
 
     @contextlib.contextmanager
     def building_plan(self):

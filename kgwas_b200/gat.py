@@ -85,9 +85,50 @@ class GATConv(nn.Module):
 
 
 class _GatMeta:
-    def __init__(self, plan: LayerPlan, node_types, h, relu, rel_scale, bip, slope, temperature, mode, want_alpha):
+    def __init__(self, plan: LayerPlan, node_types, h, relu, rel_scale, bip, slope, temperature, mode, want_alpha,
+                 shard=None):
         self.plan, self.node_types, self.h, self.relu, self.rel_scale = plan, node_types, h, relu, rel_scale
         self.bip, self.slope, self.temperature, self.mode, self.want_alpha = bip, slope, temperature, mode, want_alpha
+        # SNP-sharded execution (dist.py): rows of a shared destination type are partial sums over ranks; this rank adds
+        # the bias (and takes the bias gradient) only on the rows it owns, the ReLU runs after the cross-rank sum, and a
+        # softmax group whose in-edges come from the sharded type (SNP -> Gene) is normalised ACROSS ranks
+        self.shard = shard
+        self.root_range = shard.root_range if shard is not None else {}
+        self.sharded_type = shard.sharded_type if shard is not None else None
+
+    def fused_relu(self, T):
+        return self.relu and T not in self.root_range
+
+    def cross_rank_softmax(self, T, job):
+        return (self.shard is not None and self.mode == ATT_SOFTMAX and T in self.root_range
+                and job.src_type == self.sharded_type)
+
+
+def _seg_sum(job, v):
+    """Per softmax group: sum of a per-slot scalar (slot order), through kgb_spmm on a one-column gather table."""
+    g0, ones = job.group_sum_csr()
+    y = torch.empty((g0.n_rows, 32), dtype=torch.float32, device=v.device)
+    _lib.spmm(g0, ones, y, 32, ew=v.contiguous())
+    return y[:, 0].contiguous()
+
+
+def _global_softmax(job, alpha_loc, z_raw, temperature):
+    """alpha_loc = softmax over THIS rank's slots of each group; returns the softmax over the slots of all ranks.
+    Per group, log-sum-exp_local = sum_j alpha_j (s_j - log alpha_j) (every term equals it; the alpha-weighted mean is
+    exact and immune to underflowing alphas); the global normaliser follows from two all-reduces of [n_groups]."""
+    import torch.distributed as dist
+    s = z_raw / temperature
+    lse = _seg_sum(job, alpha_loc * s - torch.xlogy(alpha_loc, alpha_loc))
+    has = job.local_group_mask()
+    neg_inf = torch.full_like(lse, float("-inf"))
+    lse = torch.where(has, lse, neg_inf)
+    m = lse.clone()
+    dist.all_reduce(m, op=dist.ReduceOp.MAX)
+    m = torch.where(torch.isfinite(m), m, torch.zeros_like(m))
+    se = torch.exp(lse - m)
+    dist.all_reduce(se, op=dist.ReduceOp.SUM)
+    f = torch.where(has, torch.exp(lse - m - torch.log(se.clamp_min(1e-38))), torch.zeros_like(lse))
+    return alpha_loc * f[job.slot_group()]
 
 
 def _f(rows, cols, dev):
@@ -124,6 +165,8 @@ class HeteroGatLayerFn(torch.autograd.Function):
             out = _f(n_t, h, dev)
             bias_T = bias[a:b].sum(0) * scale
             jobs = plan.jobs[T]
+            shared = T in meta.root_range                 # partial rows: bias on owned rows only, ReLU after the sum
+            relu_T = meta.fused_relu(T)
             for ji, job in enumerate(jobs):
                 lo, hi, R, S = job.rel_ids[0], job.rel_ids[-1] + 1, job.R, job.src_type
                 first, last = ji == 0, ji == len(jobs) - 1
@@ -133,24 +176,31 @@ class HeteroGatLayerFn(torch.autograd.Function):
                 _lib.rowdot(x[T], Vd[lo:hi], a_d, h, R, 0)
                 alpha = torch.empty(job.n_edges, dtype=torch.float32, device=dev)
                 _lib.gat_alpha(job.gcsr, a_s, a_d, R, job.mode == "af", alpha, meta.slope, meta.temperature, meta.mode)
+                if meta.cross_rank_softmax(T, job):
+                    z_raw = torch.empty_like(alpha)
+                    _lib.gat_alpha(job.gcsr, a_s, a_d, R, job.mode == "af", z_raw, meta.slope, meta.temperature, ATT_RAW)
+                    alpha = _global_softmax(job, alpha, z_raw, meta.temperature)
                 if job.mode == "xf":
                     z = _f(job.n_src, R * h, dev)
                     _lib.gemm(KGB_NT, x[S], Wsrc[lo:hi].reshape(R * h, h), z, job.n_src, R * h, h, alpha=scale)
                     _lib.spmm(job.csr, z.view(job.n_src * R, h), out, h, ew=alpha, beta=0.0 if first else 1.0,
-                              bias=bias_T if last else None, relu=meta.relu and last)
+                              bias=bias_T if (last and not shared) else None, relu=relu_T and last)
                     A = None
                 else:
                     A = _f(n_t, R * h, dev)
                     _lib.spmm(job.csr, x[S], A.view(n_t * R, h), h, ew=alpha)
                     wcat_t = Wsrc[lo:hi].permute(1, 0, 2).reshape(h, R * h)
                     _lib.gemm(KGB_NT, A, wcat_t, out, n_t, h, R * h, alpha=scale, beta=0.0 if first else 1.0,
-                              bias=bias_T if last else None, relu=meta.relu and last)
+                              bias=bias_T if (last and not shared) else None, relu=relu_T and last)
                 saved[(T, ji)] = (a_s, a_d, alpha, A)
                 if meta.want_alpha:
                     coo = torch.empty_like(alpha)
                     coo[job.eperm.long()] = alpha                                # slot order -> COO order
                     for k, rid in enumerate(job.rel_ids):
                         alphas[rid] = coo[job.edge_offsets[k]:job.edge_offsets[k + 1]].unsqueeze(-1)
+            if shared:
+                r0, r1 = meta.root_range[T]
+                out[r0:r1] += bias_T
             outs.append(out)
         ctx.meta, ctx.saved = meta, saved
         ctx.save_for_backward(Wsrc, Wdst, As, Ad, Vs, Vd, *[x[t] for t in meta.node_types], *outs)
@@ -188,13 +238,14 @@ class HeteroGatLayerFn(torch.autograd.Function):
             a, b = plan.rel_range[T]
             scale = meta.rel_scale[T]
             n_t = plan.num_nodes[T]
-            g = _lib.relu_bwd(d_out, outs[T]) if meta.relu else d_out.contiguous()
+            g = _lib.relu_bwd(d_out, outs[T]) if meta.fused_relu(T) else d_out.contiguous()
             if scale != 1.0:
                 g = g * scale
             for i in range(a, b):
                 used[i] = True
             db = torch.empty(h, dtype=torch.float32, device=dev)
-            _lib.wcolsum(g, h, db)
+            r0, r1 = meta.root_range.get(T, (0, n_t))          # the bias lives on the rows this rank owns
+            _lib.wcolsum(g[r0:r1], h, db)
             dbias[a:b] = db
             for ji, job in enumerate(plan.jobs[T]):
                 lo, hi, R, S = job.rel_ids[0], job.rel_ids[-1] + 1, job.R, job.src_type
@@ -209,8 +260,7 @@ class HeteroGatLayerFn(torch.autograd.Function):
                     z = _f(job.n_src, R * h, dev)
                     _lib.gemm(KGB_NT, x[S], wcat, z, job.n_src, R * h, h)            # recompute H_s (small side)
                     _lib.sddmm(job.csr, g, z.view(job.n_src * R, h), h, dalpha)
-                    _lib.gat_dsoftmax(job.gcsr, a_s, a_d, R, False, alpha, dalpha, du, da_d, meta.slope,
-                                      meta.temperature, meta.mode)
+                    _dsoftmax(meta, T, job, a_s, a_d, R, False, alpha, dalpha, du, da_d)
                     dz = z                                                           # reuse the buffer
                     _lib.spmm(job.tcsr, g, dz.view(job.n_src * R, h), h, ew=alpha, wperm=job.t_eperm, ew2=du,
                               rowsum2=da_s, bins=1)
@@ -223,8 +273,7 @@ class HeteroGatLayerFn(torch.autograd.Function):
                     gp = _f(n_t, R * h, dev)
                     _lib.gemm(KGB_NN, g, wcat_t, gp, n_t, R * h, h)                  # G' = g . W_src per slot
                     _lib.sddmm(job.csr, gp.view(n_t * R, h), x[S], h, dalpha)
-                    _lib.gat_dsoftmax(job.gcsr, a_s, a_d, R, True, alpha, dalpha, du, da_d, meta.slope,
-                                      meta.temperature, meta.mode)
+                    _dsoftmax(meta, T, job, a_s, a_d, R, True, alpha, dalpha, du, da_d)
                     buf, beta = target(S)          # needed as the spmm output even if x[S] wants no grad
                     _lib.spmm(job.tcsr, gp.view(n_t * R, h), buf, h, ew=alpha, wperm=job.t_eperm, ew2=du,
                               rowsum2=da_s, bins=R, beta=beta)
@@ -263,7 +312,22 @@ class HeteroGatLayerFn(torch.autograd.Function):
         return (None, *gx, *gp_)
 
 
-def hetero_gat(convs: Dict[EdgeType, GATConv], x_dict, edge_index_dict, aggr: str, relu: bool, kwargs_dict):
+def _dsoftmax(meta, T, job, a_s, a_d, R, src_is_node, alpha, dalpha, du, da_d):
+    """Backward of the attention normalisation.  Groups that span ranks: S_g = sum_j alpha_j dalpha_j is summed over
+    ranks first, dz_j = alpha_j (dalpha_j - S_g) / T is formed here and the kernel only applies the leaky-relu slope
+    and the per-group sum (its RAW mode: dz = dalpha)."""
+    if meta.cross_rank_softmax(T, job):
+        import torch.distributed as dist
+        s_g = _seg_sum(job, alpha * dalpha)
+        dist.all_reduce(s_g, op=dist.ReduceOp.SUM)
+        dz = (alpha * (dalpha - s_g[job.slot_group()]) / meta.temperature).contiguous()
+        _lib.gat_dsoftmax(job.gcsr, a_s, a_d, R, src_is_node, alpha, dz, du, da_d, meta.slope, meta.temperature, ATT_RAW)
+    else:
+        _lib.gat_dsoftmax(job.gcsr, a_s, a_d, R, src_is_node, alpha, dalpha, du, da_d, meta.slope, meta.temperature,
+                          meta.mode)
+
+
+def hetero_gat(convs: Dict[EdgeType, GATConv], x_dict, edge_index_dict, aggr: str, relu: bool, kwargs_dict, shard=None):
     """Fused multi-relation GAT layer; mirrors HeteroConv + the patched ``group`` (kgwas/utils.py:53-71)."""
     ret = kwargs_dict.get("return_attention_weights_dict", {}) or {}
     raw = kwargs_dict.get("return_raw_attention_weights_dict", {}) or {}
@@ -272,7 +336,11 @@ def hetero_gat(convs: Dict[EdgeType, GATConv], x_dict, edge_index_dict, aggr: st
         raise NotImplementedError(f"unsupported HeteroConv kwargs for GAT: {sorted(extra)}")
     node_types = list(x_dict.keys())
     num_nodes = {t: int(v.size(0)) for t, v in x_dict.items()}
-    plan = get_plan(edge_index_dict, num_nodes, frozenset(convs.keys()))
+    if shard is not None:
+        with shard.building_plan():
+            plan = get_plan(edge_index_dict, num_nodes, frozenset(convs.keys()))
+    else:
+        plan = get_plan(edge_index_dict, num_nodes, frozenset(convs.keys()))
     if not plan.rel_order:
         return {}
     cs = [convs[et] for et in plan.rel_order]
@@ -298,13 +366,15 @@ def hetero_gat(convs: Dict[EdgeType, GATConv], x_dict, edge_index_dict, aggr: st
         a, b = plan.rel_range[T]
         rel_scale[T] = 1.0 if aggr == "sum" else 1.0 / (b - a)
     meta = _GatMeta(plan, node_types, h, relu, rel_scale, bip, float(cs[0].negative_slope), float(cs[0].temperature),
-                    mode, want[0])
+                    mode, want[0], shard)
     args = [x_dict[t] for t in node_types]
     args += [c.lin_src.weight for c in cs] + [c.att_src for c in cs] + [c.att_dst for c in cs] + [c.bias for c in cs]
     args += [c.lin_dst.weight for c, is_bip in zip(cs, bip) if is_bip]
     res = HeteroGatLayerFn.apply(meta, *args)
     nd = len(plan.dst_types)
     out = dict(zip(plan.dst_types, res[:nd]))
+    if shard is not None:
+        out = shard.combine(out, relu)     # sum the partial rows of shared node types across ranks, then ReLU
     if not want[0]:
         return out
     alphas = dict(zip(plan.rel_order, res[nd:]))

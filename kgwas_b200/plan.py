@@ -94,6 +94,27 @@ class PairJob:
                                                                       self.n_dst * self.R, self.csr.n_cols)
         return self._gcsr
 
+    def slot_group(self) -> torch.Tensor:
+        """int64 [E]: softmax / mean group (t*R + k) of every CSR slot."""
+        if getattr(self, "_slot_group", None) is None:
+            rp = self.gcsr.rowptr.long()
+            self._slot_group = torch.repeat_interleave(torch.arange(rp.numel() - 1, device=rp.device), rp[1:] - rp[:-1])
+        return self._slot_group
+
+    def local_group_mask(self) -> torch.Tensor:
+        """bool [n_groups]: the group has at least one slot on this rank."""
+        rp = self.gcsr.rowptr
+        return (rp[1:] - rp[:-1]) > 0
+
+    def group_sum_csr(self):
+        """(CSR with the group row pointers and an all-zero column array, ones[1, 32]): kgb_spmm over it with a
+        per-slot scalar as edge weight is the per-group sum of that scalar (cross-rank softmax statistics, gat.py)."""
+        if getattr(self, "_gsum", None) is None:
+            g = self.gcsr
+            self._gsum = (_lib.Csr(g.rowptr, torch.zeros_like(g.col), g.n_rows, 1),
+                          torch.ones((1, 32), dtype=torch.float32, device=g.col.device))
+        return self._gsum
+
     def __repr__(self):
         return (f"PairJob({self.src_type}->{self.dst_type}, R={self.R}, mode={self.mode}, E={self.n_edges}, "
                 f"heavy_rows={self.csr.n_hrows}/{self.tcsr.n_hrows})")

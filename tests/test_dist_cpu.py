@@ -84,3 +84,80 @@ def test_split_range_covers():
             assert spans[0][0] == 0 and spans[-1][1] == n
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             assert max(hi - lo for lo, hi in spans) - min(hi - lo for lo, hi in spans) <= 1
+
+
+class _Patch:
+    """monkeypatch-like setter for the spawned workers (no pytest fixtures there)."""
+
+    def setattr(self, obj, name, val):
+        setattr(obj, name, val)
+
+
+def _parity_worker(rank, world, port, ret, backbone, h):
+    """Sharded forward + backward on `world` gloo ranks == the single-process result, with the CUDA kernels replaced by
+    the CPU stand-ins (tests/_cpu_kernels.py): partition, owned root rows, cross-rank sums (and, for GAT, the cross-rank
+    softmax), un-fused ReLU, gradient all-reduce -- everything on the host side of the multi-GPU path."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import _cpu_kernels
+        import kgwas_b200
+        from kgwas_b200 import dist as kd, make_synth_kg
+        _cpu_kernels.install(_Patch())
+        data = make_synth_kg(scale=0.003, seed=11, hidden=h)
+        n_snp = data["SNP"].num_nodes
+        torch.manual_seed(0)
+        model = kgwas_b200.HeteroGNN(data, h, 1, 2, backbone, "sum", h, h, h, 1, no_relu=True)
+        g = torch.Generator().manual_seed(5)
+        y, w = torch.randn(n_snp, generator=g), torch.rand(n_snp, generator=g, dtype=torch.float64)
+        pred_full = model(data.x_dict, data.edge_index_dict, n_snp).reshape(-1)
+        (torch.sum(w * (pred_full - y) ** 2) / n_snp).backward()
+        lazy = torch.nn.parameter.UninitializedParameter
+        ref = {k: (None if p.grad is None else p.grad.clone()) for k, p in model.named_parameters() if not isinstance(p, lazy)}
+        model.zero_grad(set_to_none=True)
+        kgwas_b200.plan.clear_plan_cache()
+        local, shard, (lo, hi) = kd.shard_graph(data, rank, world)
+        kd.attach(model, shard)
+        pred = model(local.x_dict, local.edge_index_dict, hi - lo).reshape(-1)
+        (torch.sum(w[lo:hi] * (pred - y[lo:hi]) ** 2) / n_snp).backward()
+        kd.all_reduce_gradients([p for p in model.parameters() if not isinstance(p, lazy)])
+        err = ((pred - pred_full[lo:hi]).abs().max() / pred_full.abs().max()).item()
+        scale = max(v.abs().max().item() for v in ref.values() if v is not None)
+        gerr, none_ok = 0.0, True
+        for k, p in model.named_parameters():
+            if isinstance(p, lazy):
+                continue
+            if ref[k] is None:
+                none_ok &= p.grad is None or float(p.grad.abs().max()) == 0.0
+            else:
+                none_ok &= p.grad is not None
+                gerr = max(gerr, (p.grad - ref[k]).abs().max().item() / scale)
+        ret[rank] = (err, gerr, bool(none_ok))
+    finally:
+        dist.destroy_process_group()
+
+
+def _run_parity(backbone, h):
+    ctx = mp.get_context("spawn")
+    ret = ctx.Manager().dict()
+    port = _free_port()
+    procs = [ctx.Process(target=_parity_worker, args=(r, 2, port, ret, backbone, h)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=300)
+    assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
+    for r in range(2):
+        err, gerr, none_ok = ret[r]
+        assert err < 1e-4 and gerr < 2e-4 and none_ok, (backbone, r, err, gerr, none_ok)
+
+
+def test_sharded_sage_equals_single_process_gloo_world2():
+    _run_parity("SAGE", 32)
+
+
+def test_sharded_gat_equals_single_process_gloo_world2():
+    """incl. the softmax over SNP -> Gene groups whose in-edges are spread over the ranks"""
+    _run_parity("GAT", 32)

@@ -17,7 +17,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, ret, h):
+def _worker(rank, world, port, ret, h, backbone="SAGE"):
     import torch.distributed as dist
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
@@ -30,14 +30,15 @@ def _worker(rank, world, port, ret, h):
         data = make_synth_kg(scale=0.004, seed=11, hidden=h)
         n_snp = data["SNP"].num_nodes
         torch.manual_seed(0)
-        model = kgwas_b200.HeteroGNN(data, h, 1, 2, "SAGE", "sum", h, h, h, 1, no_relu=True).to(dev)
+        model = kgwas_b200.HeteroGNN(data, h, 1, 2, backbone, "sum", h, h, h, 1, no_relu=True).to(dev)
         g = torch.Generator().manual_seed(5)
         y, w = torch.randn(n_snp, generator=g).to(dev), torch.rand(n_snp, generator=g, dtype=torch.float64).to(dev)
         # single-GPU reference on this rank
         full = data.to(dev)
         pred_full = model(full.x_dict, full.edge_index_dict, n_snp).reshape(-1)
         (torch.sum(w * (pred_full - y) ** 2) / n_snp).backward()
-        ref_grads = {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None}
+        ref_grads = {k: p.grad.clone() for k, p in model.named_parameters()
+                     if not isinstance(p, torch.nn.parameter.UninitializedParameter) and p.grad is not None}
         model.zero_grad(set_to_none=True)
         kgwas_b200.plan.clear_plan_cache()
         # sharded
@@ -53,6 +54,8 @@ def _worker(rank, world, port, ret, h):
         gerr = 0.0
         scale = max(v.abs().max().item() for v in ref_grads.values())
         for k, p in model.named_parameters():
+            if isinstance(p, torch.nn.parameter.UninitializedParameter):
+                continue
             if k in ref_grads:
                 assert p.grad is not None, k
                 gerr = max(gerr, (p.grad - ref_grads[k]).abs().max().item() / scale)
