@@ -238,15 +238,22 @@ class HeteroGatLayerFn(torch.autograd.Function):
             a, b = plan.rel_range[T]
             scale = meta.rel_scale[T]
             n_t = plan.num_nodes[T]
-            g = _lib.relu_bwd(d_out, outs[T]) if meta.fused_relu(T) else d_out.contiguous()
-            if scale != 1.0:
-                g = g * scale
             for i in range(a, b):
                 used[i] = True
-            db = torch.empty(h, dtype=torch.float32, device=dev)
-            r0, r1 = meta.root_range.get(T, (0, n_t))          # the bias lives on the rows this rank owns
-            _lib.wcolsum(g[r0:r1], h, db)
-            dbias[a:b] = db
+            if meta.fused_relu(T):
+                # ReLU mask, aggregation scale and the bias gradient (column sums) in one pass over the rows
+                g = _f(n_t, h, dev)
+                sums = _f(2, h, dev)
+                _lib.relu_bwd_fused(g, h, dy=d_out.contiguous(), y=outs[T], scale=scale, sums=sums)
+                dbias[a:b] = sums[0]
+            else:
+                g = d_out.contiguous()
+                if scale != 1.0:
+                    g = g * scale
+                db = torch.empty(h, dtype=torch.float32, device=dev)
+                r0, r1 = meta.root_range.get(T, (0, n_t))      # the bias lives on the rows this rank owns
+                _lib.wcolsum(g[r0:r1], h, db)
+                dbias[a:b] = db
             for ji, job in enumerate(plan.jobs[T]):
                 lo, hi, R, S = job.rel_ids[0], job.rel_ids[-1] + 1, job.R, job.src_type
                 a_s, a_d, alpha, A = ctx.saved[(T, ji)]
@@ -291,7 +298,9 @@ class HeteroGatLayerFn(torch.autograd.Function):
                     _lib.rank_update(da_d, Vd[lo:hi], buf, h, R, beta)
         ctx.saved = None
         # fold the logit vectors back onto the parameters:  v = W^T att
-        bip = torch.tensor(meta.bip, device=dev)
+        bip = getattr(plan, "_bip_mask", None)        # built once per plan (a host-to-device copy: not inside a graph capture)
+        if bip is None or bip.device != dev or bip.numel() != len(meta.bip):
+            bip = plan._bip_mask = torch.tensor(meta.bip, device=dev)
         outer_s = As.unsqueeze(2) * dVs.unsqueeze(1)                                  # d W_src from a_s
         outer_d = Ad.unsqueeze(2) * dVd.unsqueeze(1)                                  # d W_dst (or W_src) from a_t
         dWsrc = dWsrc + outer_s + torch.where(bip.view(-1, 1, 1), torch.zeros_like(outer_d), outer_d)
