@@ -59,6 +59,11 @@ class _HeadFn(torch.autograd.Function):
         return d_hid, d_w, d_b
 
 
+def _head_is_fusable(w_lin) -> bool:
+    """single-output fp32 head on the GPU: evaluated in the epilogue of the last layer's last SNP-row kernel"""
+    return w_lin.size(0) == 1 and w_lin.is_cuda and w_lin.dtype == torch.float32
+
+
 class HeteroGNN(nn.Module):
     def __init__(self, pyg_data, hidden_channels, out_channels, num_layers, gnn_backbone, gnn_aggr,
                  snp_init_dim_size, gene_init_dim_size, go_init_dim_size, gat_num_head, no_relu=False):
@@ -113,8 +118,7 @@ class HeteroGNN(nn.Module):
         head, slice.  This is the region the edges-aggregated/s metric is defined on."""
         attention_all_layers = []
         w_lin = self.lin.weight
-        fuse_head = (not return_attention_weights and w_lin.size(0) == 1 and w_lin.is_cuda
-                     and w_lin.dtype == torch.float32)
+        fuse_head = not return_attention_weights and _head_is_fusable(w_lin)
         logits_all = None
         for li, conv in enumerate(self.convs):
             if return_attention_weights:                                   # model.py:65-72

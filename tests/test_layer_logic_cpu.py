@@ -130,3 +130,36 @@ def test_fused_gat_layer_host_logic_matches_oracle(monkeypatch, h, aggr):
         assert (p_r[k].grad is None) == (p_o[k].grad is None), k
         if p_r[k].grad is not None:
             assert (p_r[k].grad - p_o[k].grad).abs().max().item() <= 1e-3 * scale, k
+
+
+@pytest.mark.parametrize("bs", [90, None])
+def test_model_with_fused_head_matches_oracle(monkeypatch, bs):
+    """HeteroGNN.forward with the head evaluated inside the last layer (the GPU configuration), final ReLU on:
+    logits, head and layer gradients against the oracle; batch_size < N and == N."""
+    import kgwas_b200
+    from kgwas_b200 import make_synth_kg, model as kmodel
+    _cpu_kernels.install(monkeypatch)
+    monkeypatch.setattr(kmodel, "_head_is_fusable", lambda w: w.size(0) == 1)
+    h = 128
+    data = make_synth_kg(scale=0.002, seed=8, hidden=h)
+    n_snp = data["SNP"].x.size(0)
+    bs = n_snp if bs is None else bs
+    ref, ours = _pair(data, h, "sum", no_relu=False)
+    with torch.no_grad():                      # a positive head bias keeps the final ReLU from zeroing every logit
+        ref.lin.bias.fill_(0.5)
+        ours.lin.bias.fill_(0.5)
+    w = torch.rand(bs, dtype=torch.float64)
+    yt = torch.randn(bs)
+    outs = []
+    for model in (ref, ours):
+        out = model({k: v.clone() for k, v in data.x_dict.items()}, data.edge_index_dict, bs).reshape(-1)
+        torch.mean(w * (out - yt) ** 2).backward()
+        outs.append(out)
+    assert float(outs[0].detach().abs().max()) > 0
+    assert _rel(outs[1], outs[0]) < 1e-4
+    p_r, p_o = dict(ref.named_parameters()), dict(ours.named_parameters())
+    scale = max(p.grad.abs().max().item() for p in p_r.values() if p.grad is not None)
+    for k in p_r:
+        assert (p_r[k].grad is None) == (p_o[k].grad is None), k
+        if p_r[k].grad is not None:
+            assert (p_r[k].grad - p_o[k].grad).abs().max().item() <= 2e-4 * scale, k
