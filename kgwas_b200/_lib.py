@@ -102,9 +102,37 @@ def _stream():
 
 
 def _need_cuda(*ts):
+    """Every operand must live on the CURRENT CUDA device: the C ABI launches on the calling thread's device and on
+    that device's current stream.  The autograd Functions enter ``torch.cuda.device(x.device)`` (see ``on_device_of``),
+    so ``model.to('cuda:1')`` works without ``torch.cuda.set_device``; a direct call with a foreign tensor raises."""
+    cur = None
     for t in ts:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise KgbError("kgwas_b200 kernels need CUDA tensors (there is no CPU path); got a CPU tensor")
+        if cur is None:
+            cur = torch.cuda.current_device()
+        if t.device.index != cur:
+            raise KgbError(f"tensor on cuda:{t.device.index} but the current device is cuda:{cur}: wrap the call in "
+                           "`with torch.cuda.device(tensor.device)` (the kgwas_b200 modules do this themselves)")
+
+
+def on_device_of(fn):
+    """Decorator for autograd ``forward`` / ``backward`` staticmethods: run with the CUDA device of the first CUDA
+    tensor argument current, so that allocations, streams, events and kernel launches all agree with the data."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(*args):
+        for a in args:
+            if isinstance(a, torch.Tensor) and a.is_cuda:
+                if a.device.index != torch.cuda.current_device():
+                    with torch.cuda.device(a.device):
+                        return fn(*args)
+                break
+        return fn(*args)
+    return wrapper
 
 
 def _f32c(t, name):
@@ -290,6 +318,17 @@ def gemm(layout: int, a: torch.Tensor, b: torch.Tensor, c: torch.Tensor, m: int,
     _need_cuda(a, b, c, bias)
     _f32c(a, "gemm a"); _f32c(b, "gemm b"); _f32c(c, "gemm c")
     if m == 0 or n == 0:
+        return c
+    if k == 0:                      # empty contraction (a node type with no rows in this mini-batch): c = act(beta c + b)
+        cv = c[:m, :n]
+        if beta == 0.0:
+            cv.zero_()
+        elif beta != 1.0:
+            cv.mul_(beta)
+        if bias is not None:
+            cv.add_(bias)
+        if relu:
+            cv.clamp_(min=0)
         return c
     lib = get_lib()
     ws_bytes = lib.kgb_gemm_workspace_bytes(layout, m, n, k)

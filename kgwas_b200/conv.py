@@ -101,6 +101,7 @@ class Linear(nn.Module):
 
 class _LinearFn(torch.autograd.Function):
     @staticmethod
+    @_lib.on_device_of
     def forward(ctx, x, w, b):
         x = x.contiguous()
         out = torch.empty((x.size(0), w.size(0)), dtype=torch.float32, device=x.device)
@@ -110,6 +111,7 @@ class _LinearFn(torch.autograd.Function):
         return out
 
     @staticmethod
+    @_lib.on_device_of
     def backward(ctx, g):
         x, w = ctx.saved_tensors
         g = g.contiguous()

@@ -141,6 +141,7 @@ class HeteroGatLayerFn(torch.autograd.Function):
     outputs: out per destination type [, alpha per relation in COO order (not differentiable)]."""
 
     @staticmethod
+    @_lib.on_device_of
     def forward(ctx, meta: _GatMeta, *tensors):
         plan, h = meta.plan, meta.h
         nt, nr = len(meta.node_types), len(plan.rel_order)
@@ -210,6 +211,7 @@ class HeteroGatLayerFn(torch.autograd.Function):
         return tuple(outs)
 
     @staticmethod
+    @_lib.on_device_of
     def backward(ctx, *grads):
         meta: _GatMeta = ctx.meta
         plan, h = meta.plan, meta.h

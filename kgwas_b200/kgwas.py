@@ -60,12 +60,20 @@ class KGWAS:
     def _ld_weights(self, n_id):
         """Per-seed LDSC weights (float64, as in kgwas.py:142-143) through one vectorised lookup table
         instead of a Python dict lookup per SNP per step."""
-        if getattr(self, "_w_table", None) is None:
-            table = np.ones(len(self.data.idx2id["SNP"]), dtype=np.float64)
-            ids = np.array([self.data.id2idx["SNP"][r] for r in self.data.rs_id_to_ldsc_weight], dtype=np.int64)
-            table[ids] = np.fromiter(self.data.rs_id_to_ldsc_weight.values(), dtype=np.float64, count=len(ids))
-            self._w_table = torch.from_numpy(table)
-        return self._w_table[n_id.cpu()].to(self.device)
+        src = self.data.rs_id_to_ldsc_weight
+        if getattr(self, "_w_table", None) is None or self._w_src is not src:     # rebuilt when process_gwas_file re-ran
+            table = np.full(len(self.data.idx2id["SNP"]), np.nan, dtype=np.float64)
+            ids = np.array([self.data.id2idx["SNP"][r] for r in src], dtype=np.int64)
+            table[ids] = np.fromiter(src.values(), dtype=np.float64, count=len(ids))
+            self._w_table, self._w_src = torch.from_numpy(table).to(self.device), src
+        w = self._w_table[n_id.to(self._w_table.device)]
+        # the reference raises KeyError for a seed SNP without an LDSC weight (kgwas.py:142-143); here the NaN-initialised
+        # table makes that case fail loudly too -- on the device, without a host sync per step
+        if w.is_cuda:
+            torch._assert_async(torch.isfinite(w).all(), "KGWAS.train: a seed SNP has no LDSC weight")
+        elif bool(torch.isnan(w).any()):
+            raise KeyError(f"no LDSC weight for SNP indices {n_id[torch.isnan(w)][:5].tolist()}")
+        return w
 
     def train(self, batch_size=512, num_workers=0, lr=1e-4, weight_decay=5e-4, epoch=10, save_best_model=True,
               save_name=None, data_to_cuda=False):

@@ -6,6 +6,7 @@ from __future__ import annotations
 import torch
 import torch.nn as nn
 
+from . import _lib
 from .conv import HeteroConv, Linear, SAGEConv
 
 
@@ -30,8 +31,8 @@ class _HeadFn(torch.autograd.Function):
     """logit[i] = <h[i,:], w> + b  for the single-output head."""
 
     @staticmethod
+    @_lib.on_device_of
     def forward(ctx, hid, w, b):
-        from . import _lib
         hid = hid.contiguous()
         out = torch.empty((hid.size(0), 1), dtype=torch.float32, device=hid.device)
         _lib.rowdot(hid, w, out, w.size(1), 1, 0)
@@ -42,8 +43,8 @@ class _HeadFn(torch.autograd.Function):
         return out
 
     @staticmethod
+    @_lib.on_device_of
     def backward(ctx, g):
-        from . import _lib
         hid, w = ctx.saved_tensors
         g = g.contiguous()
         hdim = w.size(1)

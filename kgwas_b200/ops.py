@@ -227,6 +227,7 @@ class HeteroSageLayerFn(torch.autograd.Function):
     """
 
     @staticmethod
+    @_lib.on_device_of
     def forward(ctx, meta: _SageLayerCtx, *tensors):
         plan, h = meta.plan, meta.h
         nt, nr = len(meta.node_types), len(plan.rel_order)
@@ -325,6 +326,7 @@ class HeteroSageLayerFn(torch.autograd.Function):
         return tuple(outs)
 
     @staticmethod
+    @_lib.on_device_of
     def backward(ctx, *d_outs):
         meta: _SageLayerCtx = ctx.meta
         plan, h = meta.plan, meta.h

@@ -48,8 +48,18 @@ def save_model(model, config, path_dir):
 
 
 def load_pretrained(path, model):
-    # lazy (never-used) GAT lin_dst weights are stored as UninitializedParameter objects: not weights_only-safe
-    state_dict = torch.load(os.path.join(path, "model.pt"), map_location=torch.device("cpu"), weights_only=False)
+    # lazy (never-used) GAT lin_dst weights are stored as UninitializedParameter objects (as PyG does): allow-list that
+    # one class instead of unpickling arbitrary code; KGWAS_UNSAFE_LOAD=1 restores the reference's plain torch.load
+    # (kgwas/utils.py:210) for checkpoints that hold anything else
+    import torch.nn.parameter as _tp
+    file = os.path.join(path, "model.pt")
+    try:
+        with torch.serialization.safe_globals([_tp.UninitializedParameter, _tp.Parameter]):
+            state_dict = torch.load(file, map_location=torch.device("cpu"), weights_only=True)
+    except Exception:
+        if os.environ.get("KGWAS_UNSAFE_LOAD") != "1":
+            raise
+        state_dict = torch.load(file, map_location=torch.device("cpu"), weights_only=False)
     if next(iter(state_dict))[:7] == "module.":          # checkpoints written from a DataParallel wrapper
         state_dict = {k[7:]: v for k, v in state_dict.items()}
     model.load_state_dict(state_dict)

@@ -57,6 +57,78 @@ def tiny_kg(seed, h):
     return n, ei, x
 
 
+def mid_kg(seed, h, n_snp=3000, n_gene=260):
+    """A KG big enough for the kernels the benchmark runs: h % 128 == 0 -> lean gather-reduce, >= 916 SNP rows ->
+    tcgen05 GEMMs, hub genes with several hundred in-edges -> heavy-row segments and the hub-tile path."""
+    g = torch.Generator().manual_seed(seed)
+    n = {"SNP": n_snp, "Gene": n_gene, "CellularComponent": 9, "BiologicalProcess": 40, "MolecularFunction": 17}
+    spec = [(("SNP", "TSS", "Gene"), 9000), (("SNP", "eQTL", "Gene"), 5000), (("SNP", "ABC", "Gene"), 2500),
+            (("Gene", "Gene-Signaling-Gene", "Gene"), 1500), (("Gene", "Gene-Reaction-Gene", "Gene"), 900),
+            (("Gene", "Gene-Associates-BiologicalProcess", "BiologicalProcess"), 500),
+            (("Gene", "Gene-Enables-MolecularFunction", "MolecularFunction"), 300),
+            (("Gene", "Gene-NotContributes-MolecularFunction", "MolecularFunction"), 60),
+            (("Gene", "Gene-LocatedIn-CellularComponent", "CellularComponent"), 200)]
+    ei = {}
+    for et, e in spec:
+        src = torch.randint(0, n[et[0]], (e,), generator=g)
+        if et[2] == "Gene":                          # skewed destinations: a few hub genes
+            u = torch.rand(e, generator=g)
+            dst = (n["Gene"] * u ** 3).long().clamp_(max=n["Gene"] - 1)
+        else:
+            dst = torch.randint(0, n[et[2]], (e,), generator=g)
+        ei[et] = torch.stack([src, dst])
+    for et in list(ei):
+        if et[0] != et[2]:
+            ei[(et[2], "rev_" + et[1], et[0])] = ei[et].flip([0])
+    return n, ei
+
+
+def mid_features(n, h, seed):
+    from oracle.seeded import seeded_tensor
+    return {t: seeded_tensor("x." + t, (c, h), seed, 1.0) for t, c in n.items()}
+
+
+def big_cases(model_mod):
+    """Reference-executed fixtures at the benchmark's widths (weights and features are regenerated from seeds by the
+    tests, see oracle/seeded.py; the fixture holds edge lists, logits, hidden rows, loss and gradient samples)."""
+    from oracle.seeded import canonical_key, fill_parameters, grad_sample
+    for backbone, L, h in (("SAGE", 2, 128), ("GAT", 2, 128), ("GAT", 3, 256)):
+        n, eid = mid_kg(5, h)
+        x = mid_features(n, h, 11)
+        torch.manual_seed(7)
+        m = model_mod.HeteroGNN(_Graph(list(eid.keys())), h, 1, L, backbone, "sum", h, h, h, 1)
+        bs = 1500
+        m({k: v.clone() for k, v in x.items()}, eid, bs)            # materialise the lazy weights
+        with torch.no_grad():
+            for name, p in m.named_parameters():
+                if isinstance(p, torch.nn.parameter.UninitializedParameter):
+                    continue
+                scale = 1.0 / (p.size(-1) ** 0.5) if p.dim() >= 2 else 0.1
+                from oracle.seeded import seeded_tensor
+                p.copy_(seeded_tensor(canonical_key(name), p.shape, 21, scale))
+            _, hid = m({k: v.clone() for k, v in x.items()}, eid, bs, return_h=True)
+            # centre the head so that about half of the logits survive the final ReLU (model.py:86)
+            m.lin.bias.copy_(-(hid @ m.lin.weight.t()).median().reshape(1))
+        out, hid = m({k: v.clone() for k, v in x.items()}, eid, bs, return_h=True)
+        w = torch.rand(bs, dtype=torch.float64, generator=torch.Generator().manual_seed(9))
+        y = torch.randn(bs, generator=torch.Generator().manual_seed(10))
+        loss = torch.mean(w * (out.reshape(-1) - y) ** 2)
+        loss.backward()
+        shapes = {canonical_key(k): tuple(p.shape) for k, p in m.named_parameters()
+                  if not isinstance(p, torch.nn.parameter.UninitializedParameter)}
+        grads = {canonical_key(k): (None if p.grad is None else grad_sample(p.grad)) for k, p in m.named_parameters()
+                 if not isinstance(p, torch.nn.parameter.UninitializedParameter)}
+        lazy = [canonical_key(k) for k, v in m.state_dict().items()
+                if isinstance(v, torch.nn.parameter.UninitializedParameter)]
+        rec = {"num_nodes": n, "edge_index": {k: v.to(torch.int32) for k, v in eid.items()}, "batch_size": bs,
+               "feature_seed": 11, "param_seed": 21, "hidden_dim": h, "layers": L, "backbone": backbone,
+               "w": w, "y": y, "out": out.detach(), "hidden": hid.detach()[:, :16].clone(), "loss": loss.detach(),
+               "grads": grads, "lazy_keys": lazy, "param_shapes": shapes, "lin_bias": m.lin.bias.detach().clone(),
+               "frac_positive_logits": float((out > 0).float().mean())}
+        torch.save(rec, os.path.join(OUT, f"ref_mid_{backbone.lower()}_L{L}_h{h}.pt"))
+        print(backbone, L, h, "loss", float(loss.detach()), "positive logits", rec["frac_positive_logits"])
+
+
 def _state(module):
     """state_dict split into plain tensors + the keys that are still lazy (never materialised in the reference:
     e.g. GATConv.lin_dst of a same-type relation, kgwas/conv.py:136-138)."""
@@ -114,6 +186,8 @@ def main():
                 o2, att = m({k: v.clone() for k, v in x.items()}, eid, bs, return_attention_weights=True)
                 rec["att_out"], rec["att_mean"] = o2.detach(), [a.detach() for a in att]
             torch.save(rec, os.path.join(OUT, f"ref_heterognn_{backbone.lower()}_{aggr}.pt"))
+    sys.path.insert(0, ROOT)
+    big_cases(model_mod)
     print("wrote", sorted(os.listdir(OUT)))
 
 
