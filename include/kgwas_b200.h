@@ -114,13 +114,40 @@ typedef struct {
   const int32_t* hrow_grpptr; /* [n_hrows+1] prefix sum of ceil(segments / KGB_FOLD) per heavy row */
   int32_t n_hgroups;          /* hrow_grpptr[n_hrows] */
   int64_t n_edges_hint;       /* rowptr[n_rows] if known on the host, else 0: grid policy (row- vs segment-dominated) */
-  const int32_t* hitem;       /* nullable [n_hsegs][4]: work item i = (first slot, slot count, segment id, heavy-row
+  const int32_t* hitem;       /* nullable [n_hitems][4]: work item i = (first slot, slot count, segment id, heavy-row
                                  slot) in hseg_order order -- everything a warp needs to start a segment in ONE
                                  16-byte load (the lean kernel needs it when n_hsegs > 0) */
+  int32_t n_hitems;           /* entries of hitem (= n_hsegs when hitem lists every segment) */
+  /* ---- hub plan (optional; hub_n == 0: none).  The hub_n heaviest rows are reduced from shared-memory tiles of the
+   * gathered table that are staged once per CTA with 1-D TMA (cp.async.bulk), instead of one L2 / DRAM gather per
+   * edge (kgb_spmm_hub.cuh).  Used by kgb_spmm when ew == hub_ew (the weights are baked into the chunks), the lean
+   * kernel applies (h % 128 == 0, no ew2 / wperm) and ldx == h; then hitem_tail / n_hitems_tail (the work items of
+   * the NON-hub heavy rows) replace hitem / n_hitems for the pull kernel.  Built by the caller at plan time:
+   *   slots: hub row i owns virtual slots [hub_vptr[i], hub_vptr[i+1]) (a hub is cut into parts for load balance);
+   *   chunk of tile t (gathered rows [t*T, (t+1)*T)) at hub_chunks + hub_tile_off[t], 16-byte aligned:
+   *     int32 hdr[24]: hdr[w] = first record of consumer warp w (w = 0..15), hdr[16] = end; then records
+   *     {int32 (flush << 31) | (slot << 8) | (row - t*T), float weight}, sorted by (warp, slot); flush = last record
+   *     of its slot in this tile; every slot belongs to exactly one warp. */
+  int32_t hub_n;              /* hub rows */
+  int32_t hub_nv;             /* virtual slots */
+  int32_t hub_tile_rows;      /* T <= 256 */
+  int32_t hub_n_tiles;        /* ceil(n gathered rows / T) */
+  int32_t hub_n_cta;          /* CTAs of the tile kernel = partial sets in the scratch */
+  int32_t hub_chunk_cap;      /* >= largest chunk + 32 bytes, multiple of 16 */
+  int64_t hub_n_cols;         /* rows of the gathered table */
+  const int64_t* hub_tile_off; /* [hub_n_tiles + 1] */
+  const char* hub_chunks;
+  const int32_t* hub_row;     /* [hub_n] row index of each hub */
+  const int32_t* hub_vptr;    /* [hub_n + 1] */
+  const float* hub_ew;        /* the edge-weight array the chunk weights were taken from (identity = contract) */
+  const int32_t* hitem_tail;
+  int32_t n_hitems_tail;
 } kgb_csr_t;
 enum { KGB_FOLD = 64 };       /* partial sums are folded 64 at a time (two levels) by the last finisher */
 
 KGB_API size_t kgb_spmm_scratch_bytes(int32_t n_hrows, int32_t n_hsegs, int32_t n_hgroups, int32_t h);
+/* the same plus the hub plan's partial sets ([hub_n_cta][hub_nv][h] floats) when csr->hub_n > 0 */
+KGB_API size_t kgb_spmm_scratch_bytes_csr(const kgb_csr_t* csr, int32_t h);
 enum { KGB_MAX_BINS = 8 };
 KGB_API int kgb_spmm(const kgb_csr_t* csr, const float* ew, const int32_t* wperm, const float* ew2,
                      float* rowsum2, int32_t rowsum2_bins, const float* x, int64_t ldx, float* y,

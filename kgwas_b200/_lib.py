@@ -36,7 +36,13 @@ class CsrStruct(C.Structure):
                 ("n_hrows", C.c_int32), ("n_hsegs", C.c_int32), ("hrow_id", C.c_void_p),
                 ("hrow_segptr", C.c_void_p), ("hseg_hrow", C.c_void_p), ("hseg_order", C.c_void_p),
                 ("hrow_grpptr", C.c_void_p), ("n_hgroups", C.c_int32), ("n_edges_hint", C.c_int64),
-                ("hitem", C.c_void_p)]
+                ("hitem", C.c_void_p), ("n_hitems", C.c_int32),
+                # hub plan (kgb_spmm_hub.cuh; include/kgwas_b200.h)
+                ("hub_n", C.c_int32), ("hub_nv", C.c_int32), ("hub_tile_rows", C.c_int32), ("hub_n_tiles", C.c_int32),
+                ("hub_n_cta", C.c_int32), ("hub_chunk_cap", C.c_int32), ("hub_n_cols", C.c_int64),
+                ("hub_tile_off", C.c_void_p), ("hub_chunks", C.c_void_p), ("hub_row", C.c_void_p),
+                ("hub_vptr", C.c_void_p), ("hub_ew", C.c_void_p), ("hitem_tail", C.c_void_p),
+                ("n_hitems_tail", C.c_int32)]
 
 
 _P, _I32, _I64, _F, _SZ = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_size_t
@@ -53,6 +59,7 @@ SIGNATURES = {
     "kgb_csr_heavy_workspace_bytes": (_SZ, [_I32]),
     "kgb_csr_heavy_fill": (C.c_int, [_P, _I32, _I32, _I32, _I32, _P, _P, _P, _P, _SZ, _P]),
     "kgb_spmm_scratch_bytes": (_SZ, [_I32, _I32, _I32, _I32]),
+    "kgb_spmm_scratch_bytes_csr": (_SZ, [C.POINTER(CsrStruct), _I32]),
     "kgb_spmm": (C.c_int, [C.POINTER(CsrStruct), _P, _P, _P, _P, _I32, _P, _I64, _P, _I64, _I32, _F, _P, _I32, _P, _P,
                            _P, _SZ, _P]),
     "kgb_gat_scratch_bytes": (_SZ, [_I32, _I32]),
@@ -159,6 +166,7 @@ class Csr:
         self._scratch = {}
         self.hseg_order = None
         self.hitem = None
+        self.hub = None
         self._build_heavy()
         self._refresh_struct()
 
@@ -175,7 +183,18 @@ class Csr:
         self.struct = CsrStruct(_ptr(self.rowptr), _ptr(self.col), self.n_rows, self.seg_len, self.n_hrows,
                                 self.n_hsegs, _ptr(self.hrow_id), _ptr(self.hrow_segptr), _ptr(self.hseg_hrow),
                                 _ptr(self.hseg_order), _ptr(self.hrow_grpptr), self.n_hgroups, int(self.col.numel()),
-                                _ptr(self.hitem))
+                                _ptr(self.hitem), self.n_hsegs if self.hitem is not None else 0)
+        hub = self.hub
+        if hub is not None:
+            st = self.struct
+            st.hub_n, st.hub_nv, st.hub_tile_rows, st.hub_n_tiles = hub.n, hub.nv, hub.tile_rows, hub.n_tiles
+            st.hub_n_cta, st.hub_chunk_cap, st.hub_n_cols = hub.n_cta, hub.chunk_cap, self.n_cols
+            st.hub_tile_off, st.hub_chunks = _ptr(hub.tile_off), _ptr(hub.chunks)
+            st.hub_row, st.hub_vptr, st.hub_ew = _ptr(hub.row), _ptr(hub.vptr), _ptr(hub.ew)
+            # the pull kernel's work items without the hub rows' segments (same scheduling order)
+            keep = ~hub.is_hub_hrow[self.hitem[:, 3].long()]
+            hub.hitem_tail = self.hitem[keep].contiguous()
+            st.hitem_tail, st.n_hitems_tail = _ptr(hub.hitem_tail), int(hub.hitem_tail.size(0))
 
     def schedule_for_l2(self, row_bytes: int, window_bytes: int = L2_WINDOW_BYTES):
         """Order the heavy segments by the window of the gathered table they read (rows are column-sorted), so
@@ -222,14 +241,158 @@ class Csr:
         self.n_hgroups = int(grp[-1].item())
 
     def scratch(self, h: int):
-        """Per-CSR scratch for heavy-row partials (zeroed once; kernels leave the tickets zero)."""
+        """Per-CSR scratch for heavy-row partials and the hub plan's per-CTA partial sets (zeroed once; kernels leave
+        the tickets zero)."""
         if self.n_hsegs == 0:
             return None, 0
-        if h not in self._scratch:
-            nbytes = get_lib().kgb_spmm_scratch_bytes(self.n_hrows, self.n_hsegs, self.n_hgroups, h)
-            self._scratch[h] = torch.zeros(nbytes, dtype=torch.uint8, device=self.rowptr.device)
-        s = self._scratch[h]
+        key = (h, self.hub is not None)
+        if key not in self._scratch:
+            nbytes = get_lib().kgb_spmm_scratch_bytes_csr(C.byref(self.struct), h)
+            self._scratch[key] = torch.zeros(nbytes, dtype=torch.uint8, device=self.rowptr.device)
+        s = self._scratch[key]
         return s, s.numel()
+
+    # ------------------------------------------------------------------------------------------------------------
+    # hub plan: the heaviest rows reduced from shared-memory tiles (csrc/kgb_spmm_hub.cuh)
+    # ------------------------------------------------------------------------------------------------------------
+    def build_hub(self, ew: torch.Tensor, h: int, *, min_table_bytes: Optional[int] = None, tile_rows: Optional[int] = None,
+                  n_cta: Optional[int] = None, max_slots: Optional[int] = None):
+        """Plan the hub-tile path for gather-reduces with the STATIC edge weights ``ew`` (CSR slot order) at feature
+        width ``h``.  Idempotent per (ew, h).  Returns True when a plan is attached.
+
+        Chosen when the gathered table is big (>= HUB_MIN_TABLE_BYTES: it cannot live in L2, so every heavy row that
+        sweeps it is a DRAM / L2 pass of its own) and the rows are heavy enough to have about one edge per tile."""
+        if self.hub is not None and self.hub.ew is ew and self.hub.h == h:
+            return True
+        self.hub = None
+        min_table_bytes = HUB_MIN_TABLE_BYTES if min_table_bytes is None else min_table_bytes
+        if (h not in (128, 256) or self.n_hsegs == 0 or self.hitem is None or ew is None
+                or self.n_cols * h * 4 < min_table_bytes or os.environ.get("KGB_SPMM_HUB") == "0"):
+            self._refresh_struct()
+            return False
+        dev = self.rowptr.device
+        T = tile_rows or (128 if h == 128 else 64)
+        n_tiles = (self.n_cols + T - 1) // T
+        if n_cta is None:
+            n_cta = torch.cuda.get_device_properties(dev).multi_processor_count
+        n_cta = max(1, min(n_cta, n_tiles))
+        W = HUB_WARPS
+        rp = self.rowptr.long()
+        deg_h = (rp[self.hrow_id.long() + 1] - rp[self.hrow_id.long()])          # degree of every heavy row
+        order = torch.argsort(deg_h, descending=True, stable=True)
+        deg_sorted = deg_h[order].cpu().numpy()
+        # ---- how many hubs: shared memory = slots * row + 2 stages * (tile + chunk); a hub qualifies while it still has
+        # about one edge per two tiles; heavy hubs are cut into parts no bigger than half a warp's share
+        min_deg = max(self.seg_len + 1, n_tiles // 2)
+        budget = max_slots or HUB_MAX_SLOTS[h]
+        cand = int((deg_sorted >= min_deg).sum())
+        if cand == 0:
+            self._refresh_struct()
+            return False
+        n_try = min(cand, budget)
+        while True:
+            plan = self._hub_layout(ew, h, T, n_tiles, W, order, deg_sorted, n_try, budget)
+            if plan is not None:
+                break
+            if n_try == 1:
+                self._refresh_struct()
+                return False
+            n_try = max(1, n_try * 3 // 4)
+        (n_hub, nv, vptr, hub_hrow, hub_rows, tile_off, chunks, chunk_cap, n_e, slot_sorted, loads) = plan
+        is_hub_hrow = torch.zeros(self.n_hrows, dtype=torch.bool, device=dev)
+        is_hub_hrow[hub_hrow] = True
+        self.hub = _HubPlan(n=n_hub, nv=nv, tile_rows=T, n_tiles=n_tiles, n_cta=n_cta, chunk_cap=chunk_cap, h=h,
+                            tile_off=tile_off, chunks=chunks, row=hub_rows.to(torch.int32).contiguous(),
+                            vptr=torch.from_numpy(vptr).to(torch.int32).to(dev), ew=ew, is_hub_hrow=is_hub_hrow,
+                            n_edges=n_e, slot_csr=slot_sorted, warp_loads=loads)
+        self._refresh_struct()
+        return True
+
+    def _hub_layout(self, ew, h, T, n_tiles, W, order, deg_sorted, n_try, budget):
+        """Slots, warp ownership and per-tile chunks for the ``n_try`` heaviest rows (fewer if cutting the heaviest ones
+        into parts needs more than ``budget`` slots); None when the result does not fit one SM's shared memory."""
+        import numpy as np
+        dev = self.rowptr.device
+        rp = self.rowptr.long()
+        row_bytes = h * 4
+        while True:
+            d = deg_sorted[:n_try].astype(np.int64)
+            cap = max(1, int(np.ceil(d.sum() / (2.0 * W))))
+            parts = np.maximum(1, np.ceil(d / cap)).astype(np.int64)
+            if parts.sum() <= budget or n_try == 1:
+                break
+            n_try -= max(1, int(parts.sum() - budget) // 2)
+        if parts.sum() > budget:
+            return None
+        n_hub, nv = n_try, int(parts.sum())
+        hub_hrow = order[:n_hub]                                       # heavy-row slots of the hubs, heaviest first
+        vptr = np.zeros(n_hub + 1, dtype=np.int64)
+        np.cumsum(parts, out=vptr[1:])
+        # ---- slots -> warps: longest-processing-time first
+        slot_load = np.repeat(d / parts, parts)
+        slot_warp = np.zeros(nv, dtype=np.int64)
+        loads = np.zeros(W)
+        for sidx in np.argsort(-slot_load, kind="stable"):
+            w = int(np.argmin(loads))
+            slot_warp[sidx] = w
+            loads[w] += slot_load[sidx]
+        # ---- every hub edge: (tile, warp, slot, CSR slot) -> sorted records
+        hub_rows = self.hrow_id.long()[hub_hrow]                       # row index of every hub
+        starts, lens = rp[hub_rows], rp[hub_rows + 1] - rp[hub_rows]
+        n_e = int(lens.sum().item())
+        hub_of_edge = torch.repeat_interleave(torch.arange(n_hub, device=dev), lens)
+        first = torch.cumsum(lens, 0) - lens
+        rank = torch.arange(n_e, device=dev) - first[hub_of_edge]      # position inside the hub's row
+        slot_csr = starts[hub_of_edge] + rank                          # CSR slot of the edge
+        col = self.col.long()[slot_csr]
+        tile = torch.div(col, T, rounding_mode="floor")
+        parts_t = torch.from_numpy(parts).to(dev)
+        vslot = torch.from_numpy(vptr[:-1]).to(dev)[hub_of_edge] + rank % parts_t[hub_of_edge]
+        warp = torch.from_numpy(slot_warp).to(dev)[vslot]
+        key = (tile * W + warp) * nv + vslot                           # CSR slot order breaks ties (stable sort)
+        perm = torch.argsort(key, stable=True)
+        key_s, tile_s, vslot_s = key[perm], tile[perm], vslot[perm]
+        flush = torch.ones(n_e, dtype=torch.bool, device=dev)
+        flush[:-1] = key_s[1:] != key_s[:-1]
+        packed = (vslot_s << 8) | (col[perm] - tile_s * T)
+        packed = torch.where(flush, packed - (1 << 31), packed).to(torch.int32)
+        wbits = ew.contiguous()[slot_csr[perm]].view(torch.int32)
+        # ---- chunk layout: per tile [24 x int32 header | records, padded to a multiple of 2]
+        cnt_tw = torch.bincount(tile * W + warp, minlength=n_tiles * W).view(n_tiles, W)
+        cnt_t = cnt_tw.sum(1)
+        rec_pad = (cnt_t + 1) // 2 * 2
+        chunk_bytes = HUB_HDR_INTS * 4 + rec_pad * 8
+        chunk_cap = (int(chunk_bytes.max().item()) + 32 + 15) // 16 * 16
+        if nv * row_bytes + 2 * (T * row_bytes + chunk_cap) + 64 > HUB_SMEM_LIMIT:
+            return None
+        tile_off = torch.zeros(n_tiles + 1, dtype=torch.int64, device=dev)
+        torch.cumsum(chunk_bytes, 0, out=tile_off[1:])
+        total_bytes = int(tile_off[-1].item())
+        chunks = torch.zeros(total_bytes // 4 + 16, dtype=torch.int32, device=dev)     # + slack: reads past the end
+        hdr = torch.zeros((n_tiles, HUB_HDR_INTS), dtype=torch.int32, device=dev)
+        hdr[:, 1:W + 1] = torch.cumsum(cnt_tw, 1).to(torch.int32)
+        hdr[:, W + 1:] = hdr[:, W:W + 1]
+        hdr_pos = (tile_off[:-1] // 4).view(-1, 1) + torch.arange(HUB_HDR_INTS, device=dev).view(1, -1)
+        chunks[hdr_pos.reshape(-1)] = hdr.reshape(-1)
+        first_rec = torch.cumsum(cnt_t, 0) - cnt_t                     # records before this tile (sorted order)
+        rec_in_tile = torch.arange(n_e, device=dev) - first_rec[tile_s]
+        pos = tile_off[:-1][tile_s] // 4 + HUB_HDR_INTS + 2 * rec_in_tile
+        chunks[pos] = packed
+        chunks[pos + 1] = wbits
+        return (n_hub, nv, vptr, hub_hrow, hub_rows, tile_off, chunks, chunk_cap, n_e, slot_csr[perm], loads)
+
+
+class _HubPlan:
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
+        self.hitem_tail = None
+
+
+HUB_WARPS = 16                      # hub::kWarps
+HUB_HDR_INTS = 24                   # hub::kHdrInts
+HUB_SMEM_LIMIT = 232448 - 1024      # bytes of dynamic shared memory one CTA may take on sm_100
+HUB_MAX_SLOTS = {128: 176, 256: 80}
+HUB_MIN_TABLE_BYTES = 64 << 20      # gathered tables smaller than this stay L2-resident: the pull kernel is fine
 
 
 def csr_build(src: torch.Tensor, dst: torch.Tensor, n_src: int, n_dst: int, transposed: bool = True,

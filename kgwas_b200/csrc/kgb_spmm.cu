@@ -14,6 +14,7 @@
 // to finish a row (ticket counter) folds the partials in segment order => deterministic.
 #include "kgb_common.cuh"
 #include "kgb_spmm_lean.cuh"
+#include "kgb_spmm_hub.cuh"
 #include <stdlib.h>
 
 namespace kgb {
@@ -258,6 +259,40 @@ extern "C" size_t kgb_spmm_scratch_bytes(int32_t n_hrows, int32_t n_hsegs, int32
          align_up((size_t)n_hsegs * h * 4, 256) + align_up((size_t)n_hgroups * h * 4, 256) + 256;
 }
 
+extern "C" size_t kgb_spmm_scratch_bytes_csr(const kgb_csr_t* csr, int32_t h) {
+  if (!csr) return 0;
+  size_t n = kgb_spmm_scratch_bytes(csr->n_hrows, csr->n_hsegs, csr->n_hgroups, h);
+  if (csr->hub_n > 0) n += align_up((size_t)csr->hub_n_cta * csr->hub_nv * h * 4, 256);
+  return n;
+}
+
+namespace kgb {
+// the hub rows of `csr` from shared-memory tiles (kgb_spmm_hub.cuh): tile kernel + fold of the per-CTA partials
+template <int NV>
+int launch_hub(const kgb_csr_t* csr, const float* x, float* y, int64_t ldy, const lean::Epi& ep, float* partial,
+               cudaStream_t stream) {
+  constexpr int H = NV * 128;
+  const size_t smem = hub::smem_bytes(csr->hub_nv, csr->hub_tile_rows, csr->hub_chunk_cap, H);
+  static size_t configured[16] = {0};
+  int dev = 0;
+  KGB_CUDA_OK(cudaGetDevice(&dev));
+  if (dev < 16 && configured[dev] < smem) {
+    KGB_CUDA_OK(cudaFuncSetAttribute(hub::k_hub_tile<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured[dev] = smem;
+  } else if (dev >= 16) {
+    KGB_CUDA_OK(cudaFuncSetAttribute(hub::k_hub_tile<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  }
+  hub::Params p{x, csr->hub_chunks, csr->hub_tile_off, partial, (int)csr->hub_n_cols, csr->hub_tile_rows,
+                csr->hub_n_tiles, csr->hub_nv, csr->hub_chunk_cap};
+  hub::k_hub_tile<NV><<<csr->hub_n_cta, hub::kThreads, smem, stream>>>(p);
+  KGB_LAUNCH_OK();
+  hub::k_hub_fold<NV><<<csr->hub_n, hub::kFoldWarps * 32, 0, stream>>>(partial, csr->hub_n_cta, csr->hub_nv, csr->hub_row,
+                                                                      csr->hub_vptr, y, ldy, ep);
+  KGB_LAUNCH_OK();
+  return KGB_OK;
+}
+}  // namespace kgb
+
 extern "C" int kgb_spmm(const kgb_csr_t* csr, const float* ew, const int32_t* wperm, const float* ew2, float* rowsum2,
                         int32_t rowsum2_bins, const float* x, int64_t ldx, float* y, int64_t ldy, int32_t h, float beta,
                         const float* bias, int32_t relu, const float* dot_w, float* dot_out, void* scratch,
@@ -274,9 +309,10 @@ extern "C" int kgb_spmm(const kgb_csr_t* csr, const float* ew, const int32_t* wp
   KGB_REQUIRE((dot_w == nullptr) == (dot_out == nullptr), "spmm: dot_w and dot_out go together");
   KGB_REQUIRE(!dot_w || aligned16(dot_w), "spmm: dot_w must be 16-byte aligned");
   HeavyBufs hb{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  float* hub_partial = nullptr;
   if (csr->n_hsegs > 0) {
     KGB_REQUIRE(csr->hrow_grpptr && csr->n_hgroups > 0, "spmm: hrow_grpptr / n_hgroups missing");
-    const size_t need = kgb_spmm_scratch_bytes(csr->n_hrows, csr->n_hsegs, csr->n_hgroups, h);
+    const size_t need = kgb_spmm_scratch_bytes_csr(csr, h);
     if (scratch_bytes < need || !scratch) {
       set_error("spmm: scratch %zu < %zu", scratch_bytes, need);
       return KGB_ERR_WORKSPACE;
@@ -288,6 +324,7 @@ extern "C" int kgb_spmm(const kgb_csr_t* csr, const float* ew, const int32_t* wp
     hb.gpartial2 = ws.take<float>((size_t)csr->n_hgroups * KGB_MAX_BINS);
     hb.partial = ws.take<float>((size_t)csr->n_hsegs * h);
     hb.gpartial = ws.take<float>((size_t)csr->n_hgroups * h);
+    if (csr->hub_n > 0) hub_partial = ws.take<float>((size_t)csr->hub_n_cta * csr->hub_nv * h);
   }
   const EdgeW e{ew, wperm, ew2, ew2 ? rowsum2_bins : 1};
   const bool heavy_dominated = csr->n_edges_hint > 0 && 2 * (int64_t)csr->n_hsegs * csr->seg_len > csr->n_edges_hint;
@@ -295,7 +332,7 @@ extern "C" int kgb_spmm(const kgb_csr_t* csr, const float* ew, const int32_t* wp
   // KGB_SPMM_VARIANT=0 forces the generic kernel (A/B measurements: profiles/r01_spmm_variants.md)
   const char* venv = getenv("KGB_SPMM_VARIANT");   // read per call: scratch/bench_spmm.py flips it at run time
   const bool want_lean = !(venv && atoi(venv) == 0);
-  const bool lean_ok = !ew2 && !wperm && h % 128 == 0 && (csr->n_hsegs == 0 || csr->hitem);
+  const bool lean_ok = !ew2 && !wperm && h % 128 == 0 && (csr->n_hsegs == 0 || (csr->hitem && csr->n_hitems == csr->n_hsegs));
   if (dot_w && !lean_ok) {
     set_error("spmm: the dot-product epilogue needs h %% 128 == 0, no ew2 / wperm, and csr.hitem when rows are segmented");
     return KGB_ERR_UNSUPPORTED;
@@ -303,6 +340,27 @@ extern "C" int kgb_spmm(const kgb_csr_t* csr, const float* ew, const int32_t* wp
   if (lean_ok && (want_lean || dot_w)) {
     const lean::Epi lep{beta, bias, relu, dot_w, dot_out};
     const lean::Heavy lhb{hb.ticket, hb.ticket1, hb.partial, hb.gpartial};
+    // Hub plan: the heaviest rows from shared-memory tiles (TMA), everything else through the pull kernel below with
+    // the hub rows' segments left out of its item list.  KGB_SPMM_HUB=0 switches it off (A/B measurements).
+    static const char* henv = getenv("KGB_SPMM_HUB");
+    kgb_csr_t tail;
+    const bool use_hub = csr->hub_n > 0 && ew && ew == csr->hub_ew && ldx == h && (h == 128 || h == 256) && hub_partial &&
+                         !(henv && atoi(henv) == 0);
+    if (use_hub) {
+      KGB_REQUIRE(csr->hub_tile_rows > 0 && csr->hub_tile_rows <= 256 && csr->hub_chunk_cap % 16 == 0 && csr->hub_chunks &&
+                      csr->hub_tile_off && csr->hub_row && csr->hub_vptr && csr->hub_n_cta > 0,
+                  "spmm: malformed hub plan");
+      KGB_REQUIRE(hub::smem_bytes(csr->hub_nv, csr->hub_tile_rows, csr->hub_chunk_cap, h) <= 232448,
+                  "spmm: hub plan needs more shared memory than one SM has");
+      KGB_REQUIRE(csr->n_hitems_tail == 0 || csr->hitem_tail, "spmm: hitem_tail missing");
+      const int rc = h == 128 ? launch_hub<1>(csr, x, y, ldy, lep, hub_partial, stream)
+                              : launch_hub<2>(csr, x, y, ldy, lep, hub_partial, stream);
+      if (rc) return rc;
+      tail = *csr;
+      tail.hitem = csr->hitem_tail;
+      tail.n_hitems = csr->n_hitems_tail;
+      csr = &tail;
+    }
     const int64_t resident = (int64_t)kNumSMs * (h <= 128 ? 3 : h <= 384 ? 2 : 1);
     unsigned lgrid = grid;
     // Row-dominated CSRs run `waves` x the resident CTA count instead of one persistent wave: CTA slots then turn
@@ -310,8 +368,9 @@ extern "C" int kgb_spmm(const kgb_csr_t* csr, const float* ew, const int32_t* wp
     // (measured: a captured step is 7.35 ms with one wave, 6.83 ms with 8; the kernel alone loses ~3 %).
     static const char* wenv = getenv("KGB_SPMM_WAVES");
     const int waves = wenv ? atoi(wenv) : 8;
+    if (use_hub) lgrid = spmm_grid((int64_t)csr->n_hitems + csr->n_rows, h, heavy_dominated);
     if (!heavy_dominated) {
-      const int64_t all = ((int64_t)csr->n_hsegs + csr->n_rows + 7) / 8;
+      const int64_t all = ((int64_t)csr->n_hitems + csr->n_rows + 7) / 8;
       const int64_t cap = resident * (waves > 0 ? waves : 1);
       lgrid = (unsigned)(all < cap ? all : cap);
     }

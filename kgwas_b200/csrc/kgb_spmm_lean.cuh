@@ -211,14 +211,17 @@ k_spmm_lean(kgb_csr_t g, const float* __restrict__ ew, const float* __restrict__
   const int32_t* __restrict__ col = g.col;
 
   // ------------------------------------------------------------------ heavy segments (work items [0, n_hsegs))
+  // work items [0, n_items): the heavy segments this launch is responsible for (all of them, or -- when the hub rows
+  // run through hub::k_hub_tile -- the ones of the other heavy rows)
+  const int n_items = g.n_hitems;
   int item = warp0;
-  if (item < g.n_hsegs) {
+  if (item < n_items) {
     const int4* __restrict__ items = reinterpret_cast<const int4*>(g.hitem);
     int4 it = __ldg(items + item);                               // (start, length, segment, heavy row)
     Slice cur = load_slice<kHasW>(col, ew, it.x, it.y, lane);
     while (true) {
       const int nitem = item + n_warps;
-      const bool more = nitem < g.n_hsegs;
+      const bool more = nitem < n_items;
       int4 nit = make_int4(0, 0, 0, 0);
       if (more) nit = __ldg(items + nitem);
       const int seg = it.z, hr = it.w;
@@ -268,8 +271,8 @@ k_spmm_lean(kgb_csr_t g, const float* __restrict__ ew, const float* __restrict__
 
   // ------------------------------------------------------------------ rows: iteration i of this warp = row first + i*n_warps
   // (item indices continue after the segments: the warp's first row is the first element of its stride sequence
-  //  that is >= n_hsegs)
-  const int first = item - g.n_hsegs;
+  //  that is >= n_items)
+  const int first = item - n_items;
   if (first >= g.n_rows) return;
   const int cnt = (g.n_rows - 1 - first) / n_warps + 1;
   const int32_t* __restrict__ rowptr = g.rowptr;

@@ -83,6 +83,11 @@ class PairJob:
         if self._scheduled_h != h:
             self.csr.schedule_for_l2(4 * h)
             self.tcsr.schedule_for_l2(4 * h)
+            # hub rows of launches that gather from a table too big for L2 (the SNP rows: aggregate-first forward,
+            # transform-first backward) are reduced from shared-memory tiles; the mean weights are static, so they are
+            # baked into the plan (csrc/kgb_spmm_hub.cuh).  No-op for every other job.
+            self.csr.build_hub(self.w_mean, h)
+            self.tcsr.build_hub(self.w_mean_t, h)
             self._scheduled_h = h
         return self
 

@@ -107,8 +107,15 @@ def big_cases(model_mod):
                 from oracle.seeded import seeded_tensor
                 p.copy_(seeded_tensor(canonical_key(name), p.shape, 21, scale))
             _, hid = m({k: v.clone() for k, v in x.items()}, eid, bs, return_h=True)
-            # centre the head so that about half of the logits survive the final ReLU (model.py:86)
-            m.lin.bias.copy_(-(hid @ m.lin.weight.t()).median().reshape(1))
+            # centre the head so that about half of the logits survive the final ReLU (model.py:86) -- between two
+            # well separated logits, never ON one: a logit at 0 +- 1e-7 would make the ReLU mask (and with it every
+            # gradient) depend on the last bit of the arithmetic
+            pre = (hid @ m.lin.weight.t()).reshape(-1).sort().values
+            gaps = pre[1:] - pre[:-1]
+            mid = pre.numel() // 2
+            j = mid - 50 + int(gaps[mid - 50:mid + 50].argmax())
+            assert float(gaps[j]) > 1e-3 * float(pre.abs().max()), float(gaps[j])
+            m.lin.bias.copy_(-0.5 * (pre[j] + pre[j + 1]).reshape(1))
         out, hid = m({k: v.clone() for k, v in x.items()}, eid, bs, return_h=True)
         w = torch.rand(bs, dtype=torch.float64, generator=torch.Generator().manual_seed(9))
         y = torch.randn(bs, generator=torch.Generator().manual_seed(10))

@@ -21,6 +21,9 @@ class FakeCsr:
     def schedule_for_l2(self, row_bytes, window_bytes=0):
         return self
 
+    def build_hub(self, ew, h, **kw):
+        return False
+
 
 def csr_build(src, dst, n_src, n_dst, transposed=True, seg_len=128, sort_cols=False, presort_key=None):
     """Same contract as kgb_csr_build (include/kgwas_b200.h): stable edge order, optional in-row column order."""

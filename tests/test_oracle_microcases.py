@@ -56,7 +56,7 @@ def _loop_gat(x_src, x_dst, ei, Ws, Wd, a_s, a_d, bias, temperature=1.0, mode="s
     return out, torch.tensor(alpha, dtype=torch.float64)
 
 
-def _mk(seed=0, h=8):
+def _mk(seed=0, h=32):
     g = torch.Generator().manual_seed(seed)
     x_src, x_dst = torch.randn(5, h, generator=g), torch.randn(4, h, generator=g)
     # destination 3 has no in-edge (i); edge (1 -> 0) appears twice (ii)
@@ -125,7 +125,7 @@ def _gat_pair(make, dev):
 def _hetero_pair(sage_cls, hetero_cls, dev):
     """(iv) one destination type fed by three relations, aggr = sum vs mean (PyG ``group``: stack + reduce)."""
     g = torch.Generator().manual_seed(2)
-    h = 8
+    h = 32
     x = {"A": torch.randn(5, h, generator=g), "B": torch.randn(4, h, generator=g)}
     eis = {("A", "r1", "B"): torch.tensor([[0, 1, 2], [0, 0, 1]]), ("A", "r2", "B"): torch.tensor([[3, 4], [1, 2]]),
            ("B", "r3", "B"): torch.tensor([[0, 1, 2, 3], [1, 2, 3, 3]])}
