@@ -397,7 +397,9 @@ class Runner:
                    "against": "the same KG and weights run un-sharded on rank 0 (forward + backward), all per-SNP logits"}
             del ref_model, fd, xf, pf, lf
             self.full = None
-            kgwas_b200.plan.clear_plan_cache()      # drop the un-sharded plan; the sharded one is rebuilt by the warm-up
+        # EVERY rank drops its plans (rank 0 also holds the un-sharded one): the sharded plan is rebuilt by the warm-up,
+        # and building it runs collectives (global in-degrees) that all ranks must enter together
+        kgwas_b200.plan.clear_plan_cache()
         self.model.zero_grad(set_to_none=True)
         gc.collect()
         torch.cuda.empty_cache()
@@ -644,7 +646,9 @@ def ours(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        # a mismatched collective should fail in two minutes, not hold N GPUs for NCCL's default ten
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=120))
     steps, warm = args.steps, max(args.warmup, 3)
     peak, peak_src = _peak()
 

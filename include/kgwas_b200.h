@@ -142,6 +142,10 @@ typedef struct {
   const float* hub_ew;        /* the edge-weight array the chunk weights were taken from (identity = contract) */
   const int32_t* hitem_tail;
   int32_t n_hitems_tail;
+  int32_t n_mid_rows;         /* rows with 16 < degree <= seg_len if the caller knows it, else -1 (kgb_gat_*: 0 lets the
+                                 warp-per-group pass be skipped when the one-thread-per-group pass covers every row) */
+  const int32_t* mid_row_id;  /* nullable [n_mid_rows]: those rows, ascending -- the warp-per-group pass then visits only
+                                 them instead of scanning all n_rows row pointers */
 } kgb_csr_t;
 enum { KGB_FOLD = 64 };       /* partial sums are folded 64 at a time (two levels) by the last finisher */
 

@@ -42,7 +42,8 @@ class CsrStruct(C.Structure):
                 ("hub_n_cta", C.c_int32), ("hub_chunk_cap", C.c_int32), ("hub_n_cols", C.c_int64),
                 ("hub_tile_off", C.c_void_p), ("hub_chunks", C.c_void_p), ("hub_row", C.c_void_p),
                 ("hub_vptr", C.c_void_p), ("hub_ew", C.c_void_p), ("hitem_tail", C.c_void_p),
-                ("n_hitems_tail", C.c_int32)]
+                ("n_hitems_tail", C.c_int32), ("n_mid_rows", C.c_int32),
+                ("mid_row_id", C.c_void_p)]
 
 
 _P, _I32, _I64, _F, _SZ = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_size_t
@@ -151,6 +152,7 @@ def _f32c(t, name):
 # graph bookkeeping
 # ---------------------------------------------------------------------------------------------
 
+GAT_LIGHT_MAX = 16      # kLightMax of csrc/kgb_gat.cu: groups up to this size are handled by one thread
 SEG_LEN = 128           # edges per heavy-row segment (one warp each); 128 + a 24 MB window measured best on B200
 FOLD = 64               # KGB_FOLD: partials folded per level
 L2_WINDOW_BYTES = 24 << 20   # gathered-table window the resident warps should share (126 MB L2)
@@ -167,6 +169,8 @@ class Csr:
         self.hseg_order = None
         self.hitem = None
         self.hub = None
+        self.n_mid_rows = -1
+        self.mid_row_id = None
         self._build_heavy()
         self._refresh_struct()
 
@@ -184,6 +188,8 @@ class Csr:
                                 self.n_hsegs, _ptr(self.hrow_id), _ptr(self.hrow_segptr), _ptr(self.hseg_hrow),
                                 _ptr(self.hseg_order), _ptr(self.hrow_grpptr), self.n_hgroups, int(self.col.numel()),
                                 _ptr(self.hitem), self.n_hsegs if self.hitem is not None else 0)
+        self.struct.n_mid_rows = self.n_mid_rows
+        self.struct.mid_row_id = _ptr(self.mid_row_id)
         hub = self.hub
         if hub is not None:
             st = self.struct
@@ -216,6 +222,11 @@ class Csr:
         return self.col.numel()
 
     def _build_heavy(self):
+        if self.n_rows > 0:
+            deg = self.rowptr[1:] - self.rowptr[:-1]
+            mid = torch.nonzero((deg > GAT_LIGHT_MAX) & (deg <= self.seg_len)).reshape(-1).to(torch.int32)
+            self.n_mid_rows = int(mid.numel())
+            self.mid_row_id = mid.contiguous() if self.n_mid_rows > 0 else None
         if self.n_rows == 0 or self.col.numel() <= self.seg_len:
             return
         lib = get_lib()
@@ -245,7 +256,7 @@ class Csr:
         the tickets zero)."""
         if self.n_hsegs == 0:
             return None, 0
-        key = (h, self.hub is not None)
+        key = (h, (self.hub.nv, self.hub.n_cta) if self.hub is not None else None)
         if key not in self._scratch:
             nbytes = get_lib().kgb_spmm_scratch_bytes_csr(C.byref(self.struct), h)
             self._scratch[key] = torch.zeros(nbytes, dtype=torch.uint8, device=self.rowptr.device)
@@ -265,9 +276,10 @@ class Csr:
         if self.hub is not None and self.hub.ew is ew and self.hub.h == h:
             return True
         self.hub = None
+        forced = min_table_bytes is not None                         # explicit request (tests, scratch/bench_hub.py)
         min_table_bytes = HUB_MIN_TABLE_BYTES if min_table_bytes is None else min_table_bytes
         if (h not in (128, 256) or self.n_hsegs == 0 or self.hitem is None or ew is None
-                or self.n_cols * h * 4 < min_table_bytes or os.environ.get("KGB_SPMM_HUB") == "0"):
+                or self.n_cols * h * 4 < min_table_bytes or not (forced or HUB_ENABLED)):
             self._refresh_struct()
             return False
         dev = self.rowptr.device
@@ -393,6 +405,12 @@ HUB_HDR_INTS = 24                   # hub::kHdrInts
 HUB_SMEM_LIMIT = 232448 - 1024      # bytes of dynamic shared memory one CTA may take on sm_100
 HUB_MAX_SLOTS = {128: 176, 256: 80}
 HUB_MIN_TABLE_BYTES = 64 << 20      # gathered tables smaller than this stay L2-resident: the pull kernel is fine
+# Measured on B200 (profiles/r02_hub_tile.md): on kgwas-synth-v1 the tile kernel streams the 401 MB SNP table exactly once
+# (434 MB of DRAM reads for 4.02 M hub edges, 137 us) but the hub segments were the CHEAP half of the pull kernel
+# (L2-window order keeps them L2-resident): the other 3.98 M edges -- 118 k light and mid rows with uniformly random
+# sources -- still cost 331 us on their own, so hub + tail (492 us) loses to the pull kernel alone (444 us).  The path
+# is therefore opt-in (KGB_SPMM_HUB=1); it pays on graphs whose tail is small or local.
+HUB_ENABLED = os.environ.get("KGB_SPMM_HUB", "0") == "1"
 
 
 def csr_build(src: torch.Tensor, dst: torch.Tensor, n_src: int, n_dst: int, transposed: bool = True,

@@ -129,6 +129,57 @@ __global__ void k_wcolsum_stage2(const float* __restrict__ part, int n_ctas, int
   if (lane == 0) out[i] = (beta != 0.f ? beta * out[i] : 0.f) + s;
 }
 
+// a[i, s] = <x[i, :h], v[s, :]> for s < n_slots <= 8 (slot_stride == 0: one input row, several vectors -- the folded
+// attention logits of GATConv, kgwas/conv.py:150-151).  HBM-bound (one 4h-byte row per 4*n_slots bytes of output), so:
+// the vectors live in registers, two rows are in flight per warp, and the n_slots lane-partials are reduced by a
+// transposing butterfly (lane^16 keeps half of the values, lane^8 a quarter, lane^4 one; then two plain steps):
+// 9 shuffles per row instead of 5 per slot.  Lane l with (l & 3) == 0 ends up with slot ((l>>4)&1)*4 + ((l>>3)&1)*2 + ((l>>2)&1).
+template <int H>
+__global__ void __launch_bounds__(256) k_rowdot_multi(const float* __restrict__ x, int64_t ldx, int64_t n_rows, int n_slots,
+                                                      const float* __restrict__ v, float* __restrict__ a, int64_t lda) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  RowVec<H> vs[8];
+#pragma unroll
+  for (int s = 0; s < 8; ++s) {
+    vs[s].zero();
+    if (s < n_slots) vs[s].load(v + (int64_t)s * H, lane);
+  }
+  const int my_slot = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+  auto reduce_store = [&](const RowVec<H>& xr, int64_t row) {
+    float p[8];
+#pragma unroll
+    for (int s = 0; s < 8; ++s) p[s] = xr.dot(vs[s]);
+    float q[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {                       // lane^16: lower half keeps p[0..3], upper half p[4..7]
+      const float send = (lane & 16) ? p[i] : p[i + 4];
+      const float keep = (lane & 16) ? p[i + 4] : p[i];
+      q[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+    float r[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const float send = (lane & 8) ? q[i] : q[i + 2];
+      const float keep = (lane & 8) ? q[i + 2] : q[i];
+      r[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+    float t = ((lane & 4) ? r[1] : r[0]) + __shfl_xor_sync(0xffffffffu, (lane & 4) ? r[0] : r[1], 4);
+    t += __shfl_xor_sync(0xffffffffu, t, 2);
+    t += __shfl_xor_sync(0xffffffffu, t, 1);
+    if ((lane & 3) == 0 && my_slot < n_slots) a[row * lda + my_slot] = t;
+  };
+  for (int64_t row = warp0; row < n_rows; row += 2 * n_warps) {
+    RowVec<H> x0, x1;
+    x0.load_stream(x + row * ldx, lane);
+    const bool two = row + n_warps < n_rows;
+    if (two) x1.load_stream(x + (row + n_warps) * ldx, lane);
+    reduce_store(x0, row);
+    if (two) reduce_store(x1, row + n_warps);
+  }
+}
+
 // a[i, s] = <x[i, s*slot_stride : +h], v[s, :]>
 template <int H>
 __global__ void k_rowdot(const float* __restrict__ x, int64_t ldx, int64_t n_rows, int n_slots, int64_t slot_stride,
@@ -282,6 +333,18 @@ extern "C" int kgb_rowdot(const float* x, int64_t ldx, int64_t n_rows, int32_t n
   if (n_rows == 0) return KGB_OK;
   KGB_REQUIRE(x && v && a && n_slots >= 1 && lda >= n_slots, "rowdot: bad argument");
   KGB_REQUIRE(aligned16(x) && aligned16(v) && ldx % 4 == 0 && slot_stride % 4 == 0, "rowdot: alignment");
+  if (slot_stride == 0 && n_slots <= 8 && h <= 256) {
+    const unsigned grid = warp_grid((n_rows + 1) / 2, 256);
+    switch (h) {
+      case 32: k_rowdot_multi<32><<<grid, 256, 0, (cudaStream_t)stream_>>>(x, ldx, n_rows, n_slots, v, a, lda); break;
+      case 64: k_rowdot_multi<64><<<grid, 256, 0, (cudaStream_t)stream_>>>(x, ldx, n_rows, n_slots, v, a, lda); break;
+      case 128: k_rowdot_multi<128><<<grid, 256, 0, (cudaStream_t)stream_>>>(x, ldx, n_rows, n_slots, v, a, lda); break;
+      case 256: k_rowdot_multi<256><<<grid, 256, 0, (cudaStream_t)stream_>>>(x, ldx, n_rows, n_slots, v, a, lda); break;
+      default: set_error("rowdot: feature width %d unsupported", (int)h); return KGB_ERR_UNSUPPORTED;
+    }
+    KGB_LAUNCH_OK();
+    return KGB_OK;
+  }
   KGB_DISPATCH_H(h, (k_rowdot<H><<<warp_grid(n_rows, 256), 256, 0, (cudaStream_t)stream_>>>(x, ldx, n_rows, n_slots,
                                                                                          slot_stride, v, a, lda)));
   KGB_LAUNCH_OK();

@@ -54,6 +54,70 @@ __device__ __forceinline__ void seg_write_alpha(const AttArgs& p, const int32_t*
   }
 }
 
+// Groups with at most kLightMax edges: ONE THREAD per group.  A transform-first job has one group per (destination,
+// relation) -- 4.7 M groups of 1.7 edges on the KGWAS graph -- and a warp per group spends its time on bookkeeping
+// (measured: 756 us for 8 M edges); consecutive threads own consecutive slot ranges, so their loads still coalesce.
+constexpr int kLightMax = 16;
+
+__global__ void __launch_bounds__(kGatThreads)
+k_gat_alpha_light(kgb_csr_t g, AttArgs p, float* __restrict__ alpha) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < g.n_rows; row += stride) {
+    const int s = __ldg(g.rowptr + row), e = __ldg(g.rowptr + row + 1);
+    if (e == s || e - s > kLightMax) continue;
+    const int k = (int)(row % p.R);
+    const float ad = __ldg(p.a_dst + row);
+    float m = -INFINITY;
+    for (int j = s; j < e; ++j) {                       // pass 1: z (kept in alpha[j]) and its maximum
+      const int c = __ldg(g.col + j);
+      const float u = __ldg(p.a_src + (p.src_is_node ? c * p.R + k : c)) + ad;
+      const float z = lrelu(u, p.slope);
+      float a = z;
+      if (p.mode == KGB_ATT_SOFTMAX) { a = z * p.inv_t; m = fmaxf(m, a); }
+      else if (p.mode == KGB_ATT_SIGMOID) a = 1.f / (1.f + __expf(-z * p.inv_t));
+      alpha[j] = a;
+    }
+    if (p.mode != KGB_ATT_SOFTMAX) continue;
+    float l = 0.f;
+    for (int j = s; j < e; ++j) {
+      const float ex = __expf(alpha[j] - m);
+      alpha[j] = ex;
+      l += ex;
+    }
+    const float inv = 1.f / (l + 1e-16f);
+    for (int j = s; j < e; ++j) alpha[j] *= inv;
+  }
+}
+
+__global__ void __launch_bounds__(kGatThreads)
+k_gat_dsoftmax_light(kgb_csr_t g, AttArgs p, const float* __restrict__ alpha, const float* __restrict__ dalpha,
+                     float* __restrict__ du, float* __restrict__ da_dst) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < g.n_rows; row += stride) {
+    const int s = __ldg(g.rowptr + row), e = __ldg(g.rowptr + row + 1);
+    if (e - s > kLightMax) continue;
+    const int k = (int)(row % p.R);
+    float S = 0.f;
+    if (p.mode == KGB_ATT_SOFTMAX)
+      for (int j = s; j < e; ++j) S = fmaf(__ldg(alpha + j), __ldg(dalpha + j), S);
+    const float ad = e > s ? __ldg(p.a_dst + row) : 0.f;
+    float tot = 0.f;
+    for (int j = s; j < e; ++j) {
+      const float a = __ldg(alpha + j), da = __ldg(dalpha + j);
+      float dz;
+      if (p.mode == KGB_ATT_SOFTMAX) dz = a * (da - S) * p.inv_t;
+      else if (p.mode == KGB_ATT_SIGMOID) dz = a * (1.f - a) * da * p.inv_t;
+      else dz = da;
+      const int c = __ldg(g.col + j);
+      const float u = __ldg(p.a_src + (p.src_is_node ? c * p.R + k : c)) + ad;
+      const float d = u > 0.f ? dz : p.slope * dz;
+      du[j] = d;
+      tot += d;
+    }
+    da_dst[row] = tot;                                   // empty groups: 0
+  }
+}
+
 struct HeavyScratch {
   int32_t* ticket;  // [n_hrows]
   float* seg_a;     // [n_hsegs]
@@ -68,7 +132,7 @@ k_gat_alpha_a(kgb_csr_t g, AttArgs p, float* __restrict__ alpha, HeavyScratch hs
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  const int64_t n_items = (int64_t)g.n_hsegs + g.n_rows;
+  const int64_t n_items = (int64_t)g.n_hsegs + (g.mid_row_id ? g.n_mid_rows : g.n_rows);
   for (int64_t item = warp0; item < n_items; item += n_warps) {
     if (item < g.n_hsegs) {
       const int seg = g.hseg_order ? __ldg(g.hseg_order + item) : (int)item;
@@ -104,9 +168,9 @@ k_gat_alpha_a(kgb_csr_t g, AttArgs p, float* __restrict__ alpha, HeavyScratch hs
         }
       }
     } else {
-      const int row = (int)(item - g.n_hsegs);
+      const int row = g.mid_row_id ? __ldg(g.mid_row_id + (item - g.n_hsegs)) : (int)(item - g.n_hsegs);
       const int s = __ldg(g.rowptr + row), e = __ldg(g.rowptr + row + 1);
-      if (e == s || (e - s > g.seg_len && g.n_hsegs > 0)) continue;
+      if (e - s <= kLightMax || (e - s > g.seg_len && g.n_hsegs > 0)) continue;   // light: k_gat_alpha_light
       const int k = row % p.R;
       float m = 0.f, l = 0.f;
       if (p.mode == KGB_ATT_SOFTMAX) seg_stats(p, g.col, s, e, row, k, lane, m, l);
@@ -164,7 +228,7 @@ k_gat_dsoftmax_a(kgb_csr_t g, AttArgs p, const float* __restrict__ alpha, const 
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  const int64_t n_items = (int64_t)g.n_hsegs + g.n_rows;
+  const int64_t n_items = (int64_t)g.n_hsegs + (g.mid_row_id ? g.n_mid_rows : g.n_rows);
   for (int64_t item = warp0; item < n_items; item += n_warps) {
     if (item < g.n_hsegs) {
       if (p.mode != KGB_ATT_SOFTMAX) continue;  // no group statistic needed: phase B does everything
@@ -191,9 +255,9 @@ k_gat_dsoftmax_a(kgb_csr_t g, AttArgs p, const float* __restrict__ alpha, const 
         }
       }
     } else {
-      const int row = (int)(item - g.n_hsegs);
+      const int row = g.mid_row_id ? __ldg(g.mid_row_id + (item - g.n_hsegs)) : (int)(item - g.n_hsegs);
       const int s = __ldg(g.rowptr + row), e = __ldg(g.rowptr + row + 1);
-      if (e - s > g.seg_len && g.n_hsegs > 0) continue;
+      if (e - s <= kLightMax || (e - s > g.seg_len && g.n_hsegs > 0)) continue;   // light: k_gat_dsoftmax_light
       float tot = 0.f;
       if (e > s) {
         const float S = p.mode == KGB_ATT_SOFTMAX ? seg_S(alpha, dalpha, s, e, lane) : 0.f;
@@ -296,6 +360,13 @@ inline unsigned item_grid(int64_t n_items) {
   return (unsigned)(ctas < 1 ? 1 : ctas);
 }
 
+inline unsigned thread_grid(int64_t n_threads) {
+  int64_t ctas = (n_threads + kGatThreads - 1) / kGatThreads;
+  const int64_t cap = (int64_t)kNumSMs * 16;
+  if (ctas > cap) ctas = cap;
+  return (unsigned)(ctas < 1 ? 1 : ctas);
+}
+
 int check_csr(const kgb_csr_t* g, const char* who);
 
 static int carve_heavy(const kgb_csr_t* g, void* scratch, size_t bytes, HeavyScratch* hs, const char* who) {
@@ -333,8 +404,13 @@ extern "C" int kgb_gat_alpha(const kgb_csr_t* groups, const float* a_src, const 
   HeavyScratch hs;
   if (int rc = carve_heavy(groups, scratch, scratch_bytes, &hs, "gat_alpha")) return rc;
   const AttArgs p{a_src, a_dst, n_slots, src_is_node, negative_slope, 1.f / temperature, mode};
-  k_gat_alpha_a<<<item_grid((int64_t)groups->n_hsegs + groups->n_rows), kGatThreads, 0, stream>>>(*groups, p, alpha, hs);
+  k_gat_alpha_light<<<thread_grid(groups->n_rows), kGatThreads, 0, stream>>>(*groups, p, alpha);
   KGB_LAUNCH_OK();
+  if (groups->n_hsegs > 0 || groups->n_mid_rows != 0) {      // rows with more than kLightMax edges, heavy segments
+    const int64_t items = (int64_t)groups->n_hsegs + (groups->mid_row_id ? groups->n_mid_rows : groups->n_rows);
+    k_gat_alpha_a<<<item_grid(items), kGatThreads, 0, stream>>>(*groups, p, alpha, hs);
+    KGB_LAUNCH_OK();
+  }
   if (groups->n_hsegs > 0 && mode == KGB_ATT_SOFTMAX) {
     k_gat_alpha_b<<<item_grid(groups->n_hsegs), kGatThreads, 0, stream>>>(*groups, p, alpha, hs);
     KGB_LAUNCH_OK();
@@ -355,9 +431,13 @@ extern "C" int kgb_gat_dsoftmax(const kgb_csr_t* groups, const float* a_src, con
   HeavyScratch hs;
   if (int rc = carve_heavy(groups, scratch, scratch_bytes, &hs, "gat_dsoftmax")) return rc;
   const AttArgs p{a_src, a_dst, n_slots, src_is_node, negative_slope, 1.f / temperature, mode};
-  k_gat_dsoftmax_a<<<item_grid((int64_t)groups->n_hsegs + groups->n_rows), kGatThreads, 0, stream>>>(
-      *groups, p, alpha, dalpha, du, da_dst, hs);
+  k_gat_dsoftmax_light<<<thread_grid(groups->n_rows), kGatThreads, 0, stream>>>(*groups, p, alpha, dalpha, du, da_dst);
   KGB_LAUNCH_OK();
+  if (groups->n_hsegs > 0 || groups->n_mid_rows != 0) {
+    const int64_t items = (int64_t)groups->n_hsegs + (groups->mid_row_id ? groups->n_mid_rows : groups->n_rows);
+    k_gat_dsoftmax_a<<<item_grid(items), kGatThreads, 0, stream>>>(*groups, p, alpha, dalpha, du, da_dst, hs);
+    KGB_LAUNCH_OK();
+  }
   if (groups->n_hsegs > 0) {
     k_gat_dsoftmax_b<<<item_grid(groups->n_hsegs), kGatThreads, 0, stream>>>(*groups, p, alpha, dalpha, du, da_dst, hs);
     KGB_LAUNCH_OK();

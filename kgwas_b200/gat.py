@@ -17,8 +17,11 @@ from torch import Tensor
 
 from . import _lib
 from ._lib import ATT_RAW, ATT_SIGMOID, ATT_SOFTMAX, KGB_NN, KGB_NT, KGB_TN
+import functools
+
 from .conv import Linear, glorot_
-from .plan import LayerPlan, get_plan
+from .ops import _Sched
+from .plan import BIG_EDGES, BIG_ROWS, LayerPlan, get_plan
 
 EdgeType = Tuple[str, str, str]
 
@@ -138,7 +141,12 @@ def _f(rows, cols, dev):
 class HeteroGatLayerFn(torch.autograd.Function):
     """inputs: x per node type; per relation (plan.rel_order): lin_src.weight, att_src, att_dst, bias;
     then lin_dst.weight of every bipartite (src type != dst type) relation.
-    outputs: out per destination type [, alpha per relation in COO order (not differentiable)]."""
+    outputs: out per destination type [, alpha per relation in COO order (not differentiable)].
+
+    Like the SAGE layer, every launch is only RECORDED with ``ops._Sched`` (what it reads, what it writes, SNP-sized or
+    not) and issued by the scheduler: SNP-sized kernels back to back on the caller's stream, the gene / GO sized chains on
+    high-priority side streams.  Steps that need ordinary torch ops with allocations (the cross-rank softmax of a
+    sharded run) flush the recorded launches first and run on the caller's stream."""
 
     @staticmethod
     @_lib.on_device_of
@@ -159,6 +167,9 @@ class HeteroGatLayerFn(torch.autograd.Function):
         dev = Wsrc.device
         outs, saved = [], {}
         alphas: List[Optional[Tensor]] = [None] * nr
+        sch = _Sched(dev)
+        P = functools.partial
+        keep = []
         for T in plan.dst_types:
             a, b = plan.rel_range[T]
             scale = meta.rel_scale[T]
@@ -168,41 +179,65 @@ class HeteroGatLayerFn(torch.autograd.Function):
             jobs = plan.jobs[T]
             shared = T in meta.root_range                 # partial rows: bias on owned rows only, ReLU after the sum
             relu_T = meta.fused_relu(T)
+            big_T = n_t >= BIG_ROWS
             for ji, job in enumerate(jobs):
                 lo, hi, R, S = job.rel_ids[0], job.rel_ids[-1] + 1, job.R, job.src_type
                 first, last = ji == 0, ji == len(jobs) - 1
                 job.schedule(h)
+                big_S, big_e = job.n_src >= BIG_ROWS, job.n_edges >= BIG_EDGES
                 a_s, a_d = _f(job.n_src, R, dev), _f(n_t, R, dev)
-                _lib.rowdot(x[S], Vs[lo:hi], a_s, h, R, 0)
-                _lib.rowdot(x[T], Vd[lo:hi], a_d, h, R, 0)
+                vs, vd = Vs[lo:hi], Vd[lo:hi]
+                sch.run(big_S, P(_lib.rowdot, x[S], vs, a_s, h, R, 0), (x[S], vs), (a_s,), f"fwd a_s {S}->{T}", T)
+                sch.run(big_T, P(_lib.rowdot, x[T], vd, a_d, h, R, 0), (x[T], vd), (a_d,), f"fwd a_d {S}->{T}", T)
                 alpha = torch.empty(job.n_edges, dtype=torch.float32, device=dev)
-                _lib.gat_alpha(job.gcsr, a_s, a_d, R, job.mode == "af", alpha, meta.slope, meta.temperature, meta.mode)
+                sch.run(big_e, P(_lib.gat_alpha, job.gcsr, a_s, a_d, R, job.mode == "af", alpha, meta.slope,
+                                 meta.temperature, meta.mode), (a_s, a_d), (alpha,), f"fwd alpha {S}->{T}", T)
                 if meta.cross_rank_softmax(T, job):
+                    sch.join()                                       # torch ops + collectives: caller's stream
                     z_raw = torch.empty_like(alpha)
                     _lib.gat_alpha(job.gcsr, a_s, a_d, R, job.mode == "af", z_raw, meta.slope, meta.temperature, ATT_RAW)
                     alpha = _global_softmax(job, alpha, z_raw, meta.temperature)
+                beta = 0.0 if first else 1.0
+                bias_arg = bias_T if (last and not shared) else None
                 if job.mode == "xf":
                     z = _f(job.n_src, R * h, dev)
-                    _lib.gemm(KGB_NT, x[S], Wsrc[lo:hi].reshape(R * h, h), z, job.n_src, R * h, h, alpha=scale)
-                    _lib.spmm(job.csr, z.view(job.n_src * R, h), out, h, ew=alpha, beta=0.0 if first else 1.0,
-                              bias=bias_T if (last and not shared) else None, relu=relu_T and last)
+                    wcat = Wsrc[lo:hi].reshape(R * h, h)
+                    sch.run(big_S, P(_lib.gemm, KGB_NT, x[S], wcat, z, job.n_src, R * h, h, alpha=scale), (x[S], wcat), (z,),
+                            f"fwd Z {S}->{T}", T)
+                    sch.run(big_T or big_e, P(_lib.spmm, job.csr, z.view(job.n_src * R, h), out, h, ew=alpha, beta=beta,
+                                              bias=bias_arg, relu=relu_T and last),
+                            (z, alpha, out, bias_arg), (out,), f"fwd spmm xf {S}->{T}", T)
                     A = None
+                    keep.append((z, wcat))
                 else:
                     A = _f(n_t, R * h, dev)
-                    _lib.spmm(job.csr, x[S], A.view(n_t * R, h), h, ew=alpha)
+                    sch.run(big_e or big_S, P(_lib.spmm, job.csr, x[S], A.view(n_t * R, h), h, ew=alpha), (x[S], alpha), (A,),
+                            f"fwd spmm af {S}->{T}", T)
                     wcat_t = Wsrc[lo:hi].permute(1, 0, 2).reshape(h, R * h)
-                    _lib.gemm(KGB_NT, A, wcat_t, out, n_t, h, R * h, alpha=scale, beta=0.0 if first else 1.0,
-                              bias=bias_T if (last and not shared) else None, relu=relu_T and last)
+                    sch.run(big_T, P(_lib.gemm, KGB_NT, A, wcat_t, out, n_t, h, R * h, alpha=scale, beta=beta,
+                                     bias=bias_arg, relu=relu_T and last), (A, wcat_t, out, bias_arg), (out,),
+                            f"fwd gemm af {S}->{T}", T)
+                    keep.append(wcat_t)
                 saved[(T, ji)] = (a_s, a_d, alpha, A)
                 if meta.want_alpha:
                     coo = torch.empty_like(alpha)
-                    coo[job.eperm.long()] = alpha                                # slot order -> COO order
+                    eperm = job.eperm_long()
+
+                    def to_coo(coo=coo, eperm=eperm, alpha=alpha):
+                        coo[eperm] = alpha                                       # slot order -> COO order
+                    sch.run(big_e, to_coo, (alpha, eperm), (coo,), f"fwd alpha coo {S}->{T}", T)
                     for k, rid in enumerate(job.rel_ids):
                         alphas[rid] = coo[job.edge_offsets[k]:job.edge_offsets[k + 1]].unsqueeze(-1)
             if shared:
                 r0, r1 = meta.root_range[T]
-                out[r0:r1] += bias_T
+
+                def add_bias(o=out[r0:r1], bias_T=bias_T):
+                    o.add_(bias_T)
+                sch.run(big_T, add_bias, (out, bias_T), (out,), f"fwd bias {T}", T)
+            keep.append(bias_T)
             outs.append(out)
+        sch.keep.append((keep, saved, Vs, Vd))
+        sch.join()
         ctx.meta, ctx.saved = meta, saved
         ctx.save_for_backward(Wsrc, Wdst, As, Ad, Vs, Vd, *[x[t] for t in meta.node_types], *outs)
         if meta.want_alpha:
@@ -222,9 +257,12 @@ class HeteroGatLayerFn(torch.autograd.Function):
         outs = dict(zip(plan.dst_types, sv[6 + nt:]))
         need_x = dict(zip(meta.node_types, ctx.needs_input_grad[1:1 + nt]))
         dev = Wsrc.device
-        dWsrc = torch.zeros_like(Wsrc)
-        dVs, dVd = torch.zeros_like(Vs), torch.zeros_like(Vd)
-        dbias = torch.zeros((nr, h), dtype=torch.float32, device=dev)
+        # one gradient tensor per job / destination type (NOT slices of one stacked tensor): the scheduler tracks
+        # dependencies per storage, and slices of a shared buffer would chain every job behind the previous one
+        dW_parts: Dict[int, Tensor] = {}      # first relation id of the job -> [R, h, h]
+        dVs_parts: Dict[int, Tensor] = {}
+        dVd_parts: Dict[int, Tensor] = {}
+        dbias_parts: Dict[int, Tensor] = {}   # first relation id of the destination type -> [b - a, h]
         used = [False] * nr
         dx: Dict[str, Optional[Tensor]] = {t: None for t in meta.node_types}
 
@@ -234,71 +272,137 @@ class HeteroGatLayerFn(torch.autograd.Function):
                 return dx[t], 0.0
             return dx[t], 1.0
 
-        for T, d_out in zip(plan.dst_types, grads[:len(plan.dst_types)]):
+        sch = _Sched(dev)
+        P = functools.partial
+        keep = []
+        order = sorted(range(len(plan.dst_types)), key=lambda i: -plan.num_nodes[plan.dst_types[i]])
+        for T, d_out in [(plan.dst_types[i], grads[i]) for i in order]:
             if d_out is None:
                 continue
             a, b = plan.rel_range[T]
             scale = meta.rel_scale[T]
             n_t = plan.num_nodes[T]
+            big_T = n_t >= BIG_ROWS
             for i in range(a, b):
                 used[i] = True
             if meta.fused_relu(T):
                 # ReLU mask, aggregation scale and the bias gradient (column sums) in one pass over the rows
                 g = _f(n_t, h, dev)
                 sums = _f(2, h, dev)
-                _lib.relu_bwd_fused(g, h, dy=d_out.contiguous(), y=outs[T], scale=scale, sums=sums)
-                dbias[a:b] = sums[0]
+                dy = d_out.contiguous()
+
+                dbias_T = dbias_parts[a] = _f(b - a, h, dev)
+
+                def relu_bias(g=g, dy=dy, y=outs[T], scale=scale, sums=sums, dst=dbias_T):
+                    _lib.relu_bwd_fused(g, h, dy=dy, y=y, scale=scale, sums=sums)
+                    dst.copy_(sums[0].expand_as(dst))
+                sch.run(big_T, relu_bias, (dy, outs[T]), (g, sums, dbias_T), f"bwd relu {T}", T)
             else:
                 g = d_out.contiguous()
                 if scale != 1.0:
                     g = g * scale
+                sch.main_made(g)
                 db = torch.empty(h, dtype=torch.float32, device=dev)
                 r0, r1 = meta.root_range.get(T, (0, n_t))      # the bias lives on the rows this rank owns
-                _lib.wcolsum(g[r0:r1], h, db)
-                dbias[a:b] = db
+                dbias_T = dbias_parts[a] = _f(b - a, h, dev)
+
+                def bias_grad(gr=g[r0:r1], db=db, dst=dbias_T):
+                    _lib.wcolsum(gr, h, db)
+                    dst.copy_(db.expand_as(dst))
+                sch.run(big_T, bias_grad, (g,), (db, dbias_T), f"bwd bias {T}", T)
             for ji, job in enumerate(plan.jobs[T]):
                 lo, hi, R, S = job.rel_ids[0], job.rel_ids[-1] + 1, job.R, job.src_type
                 a_s, a_d, alpha, A = ctx.saved[(T, ji)]
                 E = job.n_edges
+                big_S, big_e = job.n_src >= BIG_ROWS, E >= BIG_EDGES
                 dalpha = torch.empty(E, dtype=torch.float32, device=dev)
                 du = torch.empty(E, dtype=torch.float32, device=dev)
                 da_d = _f(n_t, R, dev)
                 da_s = _f(job.n_src, R, dev)
+                dW_j = dW_parts[lo] = _f(R * h, h, dev).view(R, h, h)
+                dvs = dVs_parts[lo] = _f(R, h, dev)
+                dvd = dVd_parts[lo] = _f(R, h, dev)
+                cross = meta.cross_rank_softmax(T, job)
                 if job.mode == "xf":
                     wcat = Wsrc[lo:hi].reshape(R * h, h)
                     z = _f(job.n_src, R * h, dev)
-                    _lib.gemm(KGB_NT, x[S], wcat, z, job.n_src, R * h, h)            # recompute H_s (small side)
-                    _lib.sddmm(job.csr, g, z.view(job.n_src * R, h), h, dalpha)
-                    _dsoftmax(meta, T, job, a_s, a_d, R, False, alpha, dalpha, du, da_d)
-                    dz = z                                                           # reuse the buffer
-                    _lib.spmm(job.tcsr, g, dz.view(job.n_src * R, h), h, ew=alpha, wperm=job.t_eperm, ew2=du,
-                              rowsum2=da_s, bins=1)
-                    _lib.gemm(KGB_TN, dz, x[S], dWsrc[lo:hi].view(R * h, h), R * h, h, job.n_src)
+                    sch.run(big_S, P(_lib.gemm, KGB_NT, x[S], wcat, z, job.n_src, R * h, h), (x[S], wcat), (z,),
+                            f"bwd Z {T}->{S}", T)                                     # recompute H_s (small side)
+                    sch.run(big_T or big_e, P(_lib.sddmm, job.csr, g, z.view(job.n_src * R, h), h, dalpha), (g, z), (dalpha,),
+                            f"bwd sddmm xf {T}->{S}", T)
+                    if cross:
+                        sch.join()
+                        _dsoftmax(meta, T, job, a_s, a_d, R, False, alpha, dalpha, du, da_d)
+                    else:
+                        sch.run(big_e, P(_dsoftmax, meta, T, job, a_s, a_d, R, False, alpha, dalpha, du, da_d),
+                                (a_s, a_d, alpha, dalpha), (du, da_d), f"bwd dsoftmax {T}->{S}", T)
+                    dz = z                                                            # reuse the buffer
+                    sch.run(big_T or big_e, P(_lib.spmm, job.tcsr, g, dz.view(job.n_src * R, h), h, ew=alpha,
+                                              wperm=job.t_eperm, ew2=du, rowsum2=da_s, bins=1),
+                            (g, alpha, du), (dz, da_s), f"bwd spmm xf {T}->{S}", T)
+                    sch.run(big_S, P(_lib.gemm, KGB_TN, dz, x[S], dW_j.view(R * h, h), R * h, h, job.n_src), (dz, x[S]),
+                            (dW_j,), f"bwd dW xf {T}->{S}", T)
                     if need_x[S]:
                         buf, beta = target(S)
-                        _lib.gemm(KGB_NN, dz, wcat, buf, job.n_src, h, R * h, beta=beta)
+                        sch.run(big_S, P(_lib.gemm, KGB_NN, dz, wcat, buf, job.n_src, h, R * h, beta=beta), (dz, wcat, buf),
+                                (buf,), f"bwd dx xf {T}->{S}", T)
+                    keep.append(wcat)
                 else:
                     wcat_t = Wsrc[lo:hi].permute(1, 0, 2).reshape(h, R * h)
                     gp = _f(n_t, R * h, dev)
-                    _lib.gemm(KGB_NN, g, wcat_t, gp, n_t, R * h, h)                  # G' = g . W_src per slot
-                    _lib.sddmm(job.csr, gp.view(n_t * R, h), x[S], h, dalpha)
-                    _dsoftmax(meta, T, job, a_s, a_d, R, True, alpha, dalpha, du, da_d)
+                    sch.run(big_T, P(_lib.gemm, KGB_NN, g, wcat_t, gp, n_t, R * h, h), (g, wcat_t), (gp,),
+                            f"bwd G' af {T}->{S}", T)                                 # G' = g . W_src per slot
+                    sch.run(big_e or big_S, P(_lib.sddmm, job.csr, gp.view(n_t * R, h), x[S], h, dalpha), (gp, x[S]),
+                            (dalpha,), f"bwd sddmm af {T}->{S}", T)
+                    if cross:
+                        sch.join()
+                        _dsoftmax(meta, T, job, a_s, a_d, R, True, alpha, dalpha, du, da_d)
+                    else:
+                        sch.run(big_e, P(_dsoftmax, meta, T, job, a_s, a_d, R, True, alpha, dalpha, du, da_d),
+                                (a_s, a_d, alpha, dalpha), (du, da_d), f"bwd dsoftmax {T}->{S}", T)
                     buf, beta = target(S)          # needed as the spmm output even if x[S] wants no grad
-                    _lib.spmm(job.tcsr, gp.view(n_t * R, h), buf, h, ew=alpha, wperm=job.t_eperm, ew2=du,
-                              rowsum2=da_s, bins=R, beta=beta)
+                    sch.run(big_e or big_S, P(_lib.spmm, job.tcsr, gp.view(n_t * R, h), buf, h, ew=alpha, wperm=job.t_eperm,
+                                              ew2=du, rowsum2=da_s, bins=R, beta=beta),
+                            (gp, alpha, du, buf), (buf, da_s), f"bwd spmm af {T}->{S}", T)
                     dwt = _f(h, R * h, dev)
-                    _lib.gemm(KGB_TN, g, A, dwt, h, R * h, n_t)
-                    dWsrc[lo:hi] = dwt.view(h, R, h).permute(1, 0, 2)
+
+                    def af_wgrad(g=g, A=A, dwt=dwt, n_t=n_t, R=R, dst=dW_j):
+                        _lib.gemm(KGB_TN, g, A, dwt, h, R * h, n_t)
+                        dst.copy_(dwt.view(h, R, h).permute(1, 0, 2))
+                    sch.run(big_T, af_wgrad, (g, A), (dwt, dW_j), f"bwd dW af {T}->{S}", T)
+                    keep.append(wcat_t)
                 # node-logit paths: a_s = X_S . Vs^T, a_d = X_T . Vd^T
-                _lib.wcolsum(x[S], h, dVs[lo:hi], w=da_s, n_slots=R)
-                _lib.wcolsum(x[T], h, dVd[lo:hi], w=da_d, n_slots=R)
+                vs, vd = Vs[lo:hi], Vd[lo:hi]
+                sch.run(big_S, P(_lib.wcolsum, x[S], h, dvs, w=da_s, n_slots=R), (x[S], da_s), (dvs,), f"bwd dVs {T}->{S}", T)
+                sch.run(big_T, P(_lib.wcolsum, x[T], h, dvd, w=da_d, n_slots=R), (x[T], da_d), (dvd,), f"bwd dVd {T}->{S}", T)
                 if need_x[S]:
                     buf, beta = target(S)
-                    _lib.rank_update(da_s, Vs[lo:hi], buf, h, R, beta)
+                    sch.run(big_S, P(_lib.rank_update, da_s, vs, buf, h, R, beta), (da_s, vs, buf), (buf,),
+                            f"bwd dx a_s {T}->{S}", T)
                 if need_x[T]:
                     buf, beta = target(T)
-                    _lib.rank_update(da_d, Vd[lo:hi], buf, h, R, beta)
+                    sch.run(big_T, P(_lib.rank_update, da_d, vd, buf, h, R, beta), (da_d, vd, buf), (buf,),
+                            f"bwd dx a_d {T}->{S}", T)
+                keep.append((dalpha, du, da_d, da_s))
+        sch.keep.append((keep, ctx.saved))
+        sch.join()
         ctx.saved = None
+
+        def assemble(parts, width, shape):
+            """per-job pieces -> one [nr, ...] tensor in relation order (zeros where no gradient arrived)"""
+            pieces, pos = [], 0
+            for lo_ in sorted(parts):
+                if lo_ > pos:
+                    pieces.append(torch.zeros((lo_ - pos, *shape), dtype=torch.float32, device=dev))
+                pieces.append(parts[lo_].reshape(-1, *shape))
+                pos = lo_ + pieces[-1].size(0)
+            if pos < nr:
+                pieces.append(torch.zeros((nr - pos, *shape), dtype=torch.float32, device=dev))
+            return torch.cat(pieces) if pieces else torch.zeros((nr, *shape), dtype=torch.float32, device=dev)
+
+        dWsrc = assemble(dW_parts, h, (h, h))
+        dVs, dVd = assemble(dVs_parts, h, (h,)), assemble(dVd_parts, h, (h,))
+        dbias = assemble(dbias_parts, h, (h,))
         # fold the logit vectors back onto the parameters:  v = W^T att
         bip = getattr(plan, "_bip_mask", None)        # built once per plan (a host-to-device copy: not inside a graph capture)
         if bip is None or bip.device != dev or bip.numel() != len(meta.bip):

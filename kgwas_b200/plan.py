@@ -99,6 +99,12 @@ class PairJob:
                                                                       self.n_dst * self.R, self.csr.n_cols)
         return self._gcsr
 
+    def eperm_long(self) -> torch.Tensor:
+        """int64 copy of ``eperm`` (CSR slot -> COO edge), cached: index for the attention export."""
+        if getattr(self, "_eperm_long", None) is None:
+            self._eperm_long = self.eperm.long()
+        return self._eperm_long
+
     def slot_group(self) -> torch.Tensor:
         """int64 [E]: softmax / mean group (t*R + k) of every CSR slot."""
         if getattr(self, "_slot_group", None) is None:

@@ -56,3 +56,20 @@ def test_critical_launches_go_first():
     preds, _, order = issue_order(ops)
     assert preds[1] == {0} and preds[2] == set()
     assert order[0] == 0 and sorted(order) == [0, 1, 2, 3]
+
+
+def test_longest_chain_first_among_ready_big_launches(monkeypatch):
+    """Layer-forward shape: root GEMM (big) -> Gene->SNP gather (big, nothing waits for it); SNP->Gene gather (big) ->
+    gene-sized GEMM (small).  The gather with work behind it is issued before the one without, so the small GEMM runs
+    under a big kernel instead of after the last one."""
+    ops = [(True, ["x_snp"], ["out_snp"]),               # 0 root term of the SNP rows
+           (False, ["x_gene"], ["z"]),                    # 1 Z = X_gene W^T
+           (True, ["z", "out_snp"], ["out_snp"]),         # 2 Gene -> SNP gather-reduce
+           (False, ["x_gene"], ["out_gene"]),             # 3 root term of the gene rows
+           (True, ["x_snp"], ["A"]),                      # 4 SNP -> Gene gather-reduce
+           (False, ["A", "out_gene"], ["out_gene"])]      # 5 out_gene += A W^T
+    from kgwas_b200 import ops as _ops
+    monkeypatch.setattr(_ops, "CHAIN_PRIORITY", True)
+    _, _, order = issue_order(ops)
+    assert order.index(4) < order.index(2)
+    assert order.index(0) < order.index(2) and order.index(1) < order.index(2) and order.index(4) < order.index(5)
