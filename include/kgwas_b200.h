@@ -175,6 +175,28 @@ KGB_API int kgb_gemm(int32_t layout, const float* a, int64_t lda, const float* b
                      float beta, const float* bias, int32_t relu, void* workspace,
                      size_t workspace_bytes, kgb_stream_t stream);
 
+/* ---- full-neighbour mini-batch assembly ---------------------- */
+/* GPU replacement for the host-side sampling of NeighborLoader(data, num_neighbors=[-1]*L, input_nodes=('SNP', ids),
+ * batch_size) (kgwas/kgwas.py:99-113; third-party C++ in the reference): L-hop frontier expansion with bit-exact node /
+ * edge bookkeeping (oracle/bookkeeping.py: full_neighbor_subgraph_ref).  The in-adjacency of a relation is the
+ * destination-major CSR kgb_csr_build returns (rowptr, col = sources, eperm = original edge ids, stable edge order).
+ *   kgb_frontier_count : offsets[i] = number of in-edges of frontier[0..i) ([n_f + 1]); *h_total (HOST) = their sum.
+ *   kgb_frontier_expand: for every frontier node in order, all its in-edges in edge order: eids[s], srcs[s], s < total.
+ *   kgb_frontier_add   : candidates cand[0..n) (sources of the expanded edges, or the seeds); those whose local id is
+ *                        still -1 get ids count_base, count_base+1, ... in FIRST-OCCURRENCE order: local[v] is set,
+ *                        new_nodes[0..n_new) lists them in that order, *h_n_new (HOST) = n_new.  firstpos is a scratch
+ *                        table [n_nodes of that type], all INT32_MAX on entry and again on exit.
+ * kgb_frontier_count / kgb_frontier_add synchronise the stream once (a size has to reach the host). */
+KGB_API size_t kgb_frontier_workspace_bytes(int64_t n);
+KGB_API int kgb_frontier_count(const int32_t* ptr, const int32_t* frontier, int32_t n_f, int32_t* offsets,
+                               int32_t* h_total, void* workspace, size_t workspace_bytes, kgb_stream_t stream);
+KGB_API int kgb_frontier_expand(const int32_t* ptr, const int32_t* col, const int32_t* eperm, const int32_t* frontier,
+                                const int32_t* offsets, int32_t n_f, int32_t total, int32_t* eids, int32_t* srcs,
+                                kgb_stream_t stream);
+KGB_API int kgb_frontier_add(const int32_t* cand, int32_t n, int32_t* local, int32_t* firstpos, int32_t count_base,
+                             int32_t* new_nodes, int32_t* h_n_new, void* workspace, size_t workspace_bytes,
+                             kgb_stream_t stream);
+
 /* ---- small fused elementwise / reduction helpers ---------------------------------- */
 /* g[i] = dy[i] * (y[i] > 0)          backward of `x.relu()` (kgwas/model.py:75)          */
 KGB_API int kgb_relu_bwd(const float* dy, const float* y, float* g, int64_t n, kgb_stream_t stream);

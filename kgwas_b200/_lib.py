@@ -78,6 +78,10 @@ SIGNATURES = {
     "kgb_rowdot": (C.c_int, [_P, _I64, _I64, _I32, _I32, _I64, _P, _P, _I64, _P]),
     "kgb_rank_update": (C.c_int, [_P, _I64, _I32, _P, _P, _I64, _I64, _I32, _F, _P]),
     "kgb_permute_f32": (C.c_int, [_P, _P, _P, _I64, _P]),
+    "kgb_frontier_workspace_bytes": (_SZ, [_I64]),
+    "kgb_frontier_count": (C.c_int, [_P, _P, _I32, _P, C.POINTER(C.c_int32), _P, _SZ, _P]),
+    "kgb_frontier_expand": (C.c_int, [_P, _P, _P, _P, _P, _I32, _I32, _P, _P, _P]),
+    "kgb_frontier_add": (C.c_int, [_P, _I32, _P, _P, _I32, _P, C.POINTER(C.c_int32), _P, _SZ, _P]),
 }
 
 
@@ -667,3 +671,52 @@ def gat_dsoftmax(groups: Csr, a_src, a_dst, n_slots: int, src_is_node: bool, alp
                                       _ptr(alpha), _ptr(dalpha), _ptr(du), _ptr(da_dst), slope, temperature, mode,
                                       _ptr(scratch), nbytes, _stream()), "kgb_gat_dsoftmax")
     return du, da_dst
+
+
+# ---------------------------------------------------------------------------------------------
+# full-neighbour frontier expansion (csrc/kgb_sampler.cu)
+# ---------------------------------------------------------------------------------------------
+
+
+def frontier_expand(ptr, col, eperm, frontier):
+    """All in-edges of the frontier nodes (frontier order, then edge order): (edge ids int32 [total], sources int32
+    [total]).  One host sync (the total has to size the outputs)."""
+    _need_cuda(ptr, col, eperm, frontier)
+    n_f = int(frontier.numel())
+    dev = ptr.device
+    i32 = dict(dtype=torch.int32, device=dev)
+    if n_f == 0:
+        return torch.empty(0, **i32), torch.empty(0, **i32)
+    lib = get_lib()
+    offsets = torch.empty(n_f + 1, **i32)
+    ws = _workspace(lib.kgb_frontier_workspace_bytes(n_f), dev)
+    total = C.c_int32(0)
+    global launches
+    launches += 1
+    _check(lib.kgb_frontier_count(_ptr(ptr), _ptr(frontier), n_f, _ptr(offsets), C.byref(total), _ptr(ws), ws.numel(),
+                                  _stream()), "kgb_frontier_count")
+    t = int(total.value)
+    eids, srcs = torch.empty(t, **i32), torch.empty(t, **i32)
+    if t:
+        launches += 1
+        _check(lib.kgb_frontier_expand(_ptr(ptr), _ptr(col), _ptr(eperm), _ptr(frontier), _ptr(offsets), n_f, t,
+                                       _ptr(eids), _ptr(srcs), _stream()), "kgb_frontier_expand")
+    return eids, srcs
+
+
+def frontier_add(cand, local, firstpos, count_base: int):
+    """Give the not-yet-seen candidates the next local ids in first-occurrence order; returns them (int32 [n_new])."""
+    _need_cuda(cand, local, firstpos)
+    n = int(cand.numel())
+    dev = local.device
+    if n == 0:
+        return torch.empty(0, dtype=torch.int32, device=dev)
+    lib = get_lib()
+    new_nodes = torch.empty(min(n, int(local.numel())), dtype=torch.int32, device=dev)
+    ws = _workspace(lib.kgb_frontier_workspace_bytes(n), dev)
+    n_new = C.c_int32(0)
+    global launches
+    launches += 1
+    _check(lib.kgb_frontier_add(_ptr(cand), n, _ptr(local), _ptr(firstpos), count_base, _ptr(new_nodes), C.byref(n_new),
+                                _ptr(ws), ws.numel(), _stream()), "kgb_frontier_add")
+    return new_nodes[:int(n_new.value)]

@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 OUT = os.path.join(os.path.dirname(HERE), "libkgwas_b200.so")
-SOURCES = ["kgb_api.cu", "kgb_csr.cu", "kgb_spmm.cu", "kgb_gemm_ffma.cu", "kgb_gemm_tc.cu", "kgb_elem.cu", "kgb_gat.cu"]
+SOURCES = ["kgb_api.cu", "kgb_csr.cu", "kgb_spmm.cu", "kgb_gemm_ffma.cu", "kgb_gemm_tc.cu", "kgb_elem.cu", "kgb_gat.cu", "kgb_sampler.cu"]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--expt-relaxed-constexpr",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-I", os.path.join(ROOT, "include"), "-I", HERE]
 

@@ -100,6 +100,77 @@ class FullNeighborSampler:
         return node_ids, sub_edges, edge_ids
 
 
+class GpuFullNeighborSampler:
+    """The same L-hop expansion on the GPU (csrc/kgb_sampler.cu through the C ABI): per hop and relation -- in the
+    reference's order, the local-id table updated after every relation -- ``kgb_frontier_count`` /
+    ``kgb_frontier_expand`` list every in-edge of the frontier and ``kgb_frontier_add`` hands out batch-local ids in
+    first-occurrence order.  Node lists, kept edge ids and relabelled edges are bit-identical to ``FullNeighborSampler``
+    (tests/test_sampler_gpu.py); they stay on the device, so a batch is assembled without the host touching the graph."""
+
+    def __init__(self, data: HeteroData, num_hops: int):
+        from . import _lib
+        self._lib = _lib
+        self.num_hops = num_hops
+        self.num_nodes = {t: data[t].num_nodes for t in data.node_types}
+        self.edge_types: List[EdgeType] = list(data.edge_types)
+        self.edges = {et: data[et].edge_index for et in self.edge_types}
+        dev = next(iter(self.edges.values())).device
+        self.device = dev
+        self.adj = {}
+        for et in self.edge_types:
+            ei = self.edges[et]
+            csr, eperm, _, _ = _lib.csr_build(ei[0], ei[1], self.num_nodes[et[0]], self.num_nodes[et[2]], transposed=False)
+            self.adj[et] = (csr.rowptr, csr.col, eperm)                 # in-edges of a node in original edge order
+        self.local = {t: torch.full((n,), -1, dtype=torch.int32, device=dev) for t, n in self.num_nodes.items()}
+        self.firstpos = {t: torch.full((n,), 2 ** 31 - 1, dtype=torch.int32, device=dev) for t, n in self.num_nodes.items()}
+
+    def sample(self, seed_type: str, seeds):
+        lib, dev = self._lib, self.device
+        seeds = torch.as_tensor(seeds, device=dev).to(torch.int32).contiguous()
+        count = {t: 0 for t in self.num_nodes}
+        nodes: Dict[str, List[torch.Tensor]] = {t: [] for t in self.num_nodes}
+
+        def add(t, cand):
+            new = lib.frontier_add(cand, self.local[t], self.firstpos[t], count[t])
+            if new.numel():
+                count[t] += int(new.numel())
+                nodes[t].append(new)
+            return new
+
+        empty = torch.empty(0, dtype=torch.int32, device=dev)
+        frontier = {t: empty for t in self.num_nodes}
+        frontier[seed_type] = add(seed_type, seeds)
+        kept: Dict[EdgeType, List[torch.Tensor]] = {et: [] for et in self.edge_types}
+        for _ in range(self.num_hops):
+            new_frontier: Dict[str, List[torch.Tensor]] = {t: [] for t in self.num_nodes}
+            for et in self.edge_types:
+                s_t, _, d_t = et
+                if frontier[d_t].numel() == 0:
+                    continue
+                ptr, col, eperm = self.adj[et]
+                eids, srcs = lib.frontier_expand(ptr, col, eperm, frontier[d_t])
+                kept[et].append(eids)
+                new = add(s_t, srcs)
+                if new.numel():
+                    new_frontier[s_t].append(new)
+            frontier = {t: (torch.cat(v) if v else empty) for t, v in new_frontier.items()}
+        node_ids = {t: (torch.cat(v) if v else empty).long() for t, v in nodes.items()}
+        sub_edges, edge_ids = {}, {}
+        for et in self.edge_types:
+            s_t, _, d_t = et
+            ids = (torch.cat(kept[et]) if kept[et] else empty).long()
+            edge_ids[et] = ids
+            ei = self.edges[et]
+            if ids.numel():
+                sub_edges[et] = torch.stack([self.local[s_t][ei[0][ids]].long(), self.local[d_t][ei[1][ids]].long()])
+            else:
+                sub_edges[et] = torch.zeros((2, 0), dtype=torch.int64, device=dev)
+        for t, ids in node_ids.items():                 # leave the local-id tables clean for the next batch
+            if ids.numel():
+                self.local[t][ids] = -1
+        return node_ids, sub_edges, edge_ids
+
+
 class NeighborLoader:
     """Iterable of ``HeteroData`` mini-batches (same constructor keywords KGWAS passes)."""
 
@@ -113,9 +184,11 @@ class NeighborLoader:
         self.seed_type, ids = input_nodes
         self.ids = np.asarray(ids.cpu() if torch.is_tensor(ids) else ids, dtype=np.int64)
         self.batch_size, self.drop_last = batch_size, drop_last
-        cpu = data if not any(t.is_cuda for t in data.edge_index_dict.values()) else data.to("cpu")
-        self.sampler = FullNeighborSampler(cpu, len(num_neighbors))
-        self._store_device = {t: data[t] for t in data.node_types}
+        on_gpu = any(t.is_cuda for t in data.edge_index_dict.values())
+        # graph resident on the GPU (KGWAS.train(data_to_cuda=True), kgwas.py:96-97): the batches are assembled there
+        self.sampler = GpuFullNeighborSampler(data, len(num_neighbors)) if on_gpu else \
+            FullNeighborSampler(data, len(num_neighbors))
+        self.on_gpu = on_gpu
 
     def __len__(self):
         n = len(self.ids)
@@ -127,10 +200,11 @@ class NeighborLoader:
 
     def make_batch(self, seeds: np.ndarray) -> HeteroData:
         node_ids, sub_edges, edge_ids = self.sampler.sample(self.seed_type, seeds)
+        as_t = (lambda a: a) if self.on_gpu else torch.from_numpy
         batch = HeteroData()
         for t in self.data.node_types:
             store = self.data[t]
-            idx = torch.from_numpy(node_ids[t])
+            idx = as_t(node_ids[t])
             for key, val in store.items():
                 if torch.is_tensor(val) and val.dim() >= 1 and val.size(0) == store.num_nodes:
                     batch[t][key] = val[idx.to(val.device)]
@@ -139,6 +213,6 @@ class NeighborLoader:
         batch[self.seed_type].batch_size = int(len(seeds))
         batch[self.seed_type].input_id = torch.from_numpy(np.asarray(seeds))
         for et in self.data.edge_types:
-            batch[et].edge_index = torch.from_numpy(sub_edges[et])
-            batch[et].e_id = torch.from_numpy(edge_ids[et])
+            batch[et].edge_index = as_t(sub_edges[et])
+            batch[et].e_id = as_t(edge_ids[et])
         return batch

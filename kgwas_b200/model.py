@@ -7,12 +7,69 @@ import torch
 import torch.nn as nn
 
 from . import _lib
+from ._lib import KGB_NN, KGB_NT, KGB_TN
 from .conv import HeteroConv, Linear, SAGEConv
 
 
+class _MlpFn(torch.autograd.Function):
+    """SimpleMLP (kgwas/model.py:10-22) on the engine's kernels: three kgb_gemm calls with the bias and the ReLU in the
+    GEMM epilogue; backward = input-gradient / weight-gradient GEMMs, the ReLU mask and the bias column sums fused in one
+    pass per hidden layer (kgb_relu_bwd_fused)."""
+
+    @staticmethod
+    @_lib.on_device_of
+    def forward(ctx, x, w1, b1, w2, b2, w3, b3):
+        x = x.contiguous()
+        n, hid, out_dim = x.size(0), w1.size(0), w3.size(0)
+        h1 = torch.empty((n, hid), dtype=torch.float32, device=x.device)
+        h2 = torch.empty((n, hid), dtype=torch.float32, device=x.device)
+        out = torch.empty((n, out_dim), dtype=torch.float32, device=x.device)
+        _lib.gemm(KGB_NT, x, w1, h1, n, hid, x.size(1), bias=b1, relu=True)
+        _lib.gemm(KGB_NT, h1, w2, h2, n, hid, hid, bias=b2, relu=True)
+        _lib.gemm(KGB_NT, h2, w3, out, n, out_dim, hid, bias=b3)
+        ctx.save_for_backward(x, w1, w2, w3, h1, h2)
+        return out
+
+    @staticmethod
+    @_lib.on_device_of
+    def backward(ctx, g):
+        x, w1, w2, w3, h1, h2 = ctx.saved_tensors
+        g = g.contiguous()
+        n, hid, out_dim = x.size(0), w1.size(0), w3.size(0)
+        dev = x.device
+        need = ctx.needs_input_grad
+
+        def new(*shape):
+            return torch.empty(shape, dtype=torch.float32, device=dev)
+        dw3, db3 = new(out_dim, hid), new(out_dim)
+        _lib.gemm(KGB_TN, g, h2, dw3, out_dim, hid, n)
+        _lib.wcolsum(g, out_dim, db3)
+        g2 = new(n, hid)
+        _lib.gemm(KGB_NN, g, w3, g2, n, hid, out_dim)
+        s2, g2m = new(2, hid), new(n, hid)
+        _lib.relu_bwd_fused(g2m, hid, dy=g2, y=h2, sums=s2)           # ReLU mask + bias gradient in one pass
+        g2 = g2m
+        dw2 = new(hid, hid)
+        _lib.gemm(KGB_TN, g2, h1, dw2, hid, hid, n)
+        g1 = new(n, hid)
+        _lib.gemm(KGB_NN, g2, w2, g1, n, hid, hid)
+        s1, g1m = new(2, hid), new(n, hid)
+        _lib.relu_bwd_fused(g1m, hid, dy=g1, y=h1, sums=s1)
+        g1 = g1m
+        dw1 = new(hid, x.size(1))
+        _lib.gemm(KGB_TN, g1, x, dw1, hid, x.size(1), n)
+        dx = None
+        if need[0]:
+            dx = new(n, x.size(1))
+            _lib.gemm(KGB_NN, g1, w1, dx, n, x.size(1), hid)
+        return dx, dw1, s1[0].clone(), dw2, s2[0].clone(), dw3, db3
+
+
 class SimpleMLP(nn.Module):
-    """kgwas/model.py:10-22.  Dense GEMMs on the raw features: kept on torch.nn.Linear (cuBLAS) --
-    adjacent to the hot path, SURVEY.md section 8 f-1."""
+    """kgwas/model.py:10-22: same sub-module names (``FC_hidden`` / ``FC_hidden2`` / ``FC_output``), hence the same
+    state-dict keys; the ``nn.Linear`` modules only hold the parameters.  CUDA fp32 inputs of a supported shape run on
+    the engine's GEMM (bias + ReLU in the epilogue); anything else -- CPU tensors (config 1,
+    the plumbing run), widths the GEMM cannot take -- goes through ``torch.nn.functional.linear``."""
 
     def __init__(self, input_dim, hidden_dim, output_dim):
         super().__init__()
@@ -21,10 +78,21 @@ class SimpleMLP(nn.Module):
         self.FC_output = nn.Linear(hidden_dim, output_dim)
         self.ReLU = nn.ReLU()
 
+    def _engine_ok(self, x):
+        dims = (x.size(-1), self.FC_hidden.out_features, self.FC_output.out_features)
+        return (x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and x.size(0) > 0 and USE_ENGINE_MLP
+                and all(d % 4 == 0 for d in dims) and self.FC_hidden.out_features in (32, 64, 128, 256, 384, 512))
+
     def forward(self, x):
+        if self._engine_ok(x):
+            return _MlpFn.apply(x, self.FC_hidden.weight, self.FC_hidden.bias, self.FC_hidden2.weight,
+                                self.FC_hidden2.bias, self.FC_output.weight, self.FC_output.bias)
         h = self.ReLU(self.FC_hidden(x))
         h = self.ReLU(self.FC_hidden2(h))
         return self.FC_output(h)
+
+
+USE_ENGINE_MLP = True
 
 
 class _HeadFn(torch.autograd.Function):

@@ -1,0 +1,43 @@
+"""GPU: the input MLPs (kgwas/model.py:10-22) on the engine's GEMM -- forward, input gradient
+and every parameter gradient against an fp64 torch.nn reference with the same weights, at the fast-mode raw widths
+(SNP 20, Gene 5120, GO 128) and one width the GEMM cannot take (70: falls back to torch, same results)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("n,in_dim,hid", [(3001, 20, 128), (2037, 5120, 128), (777, 128, 128), (1500, 128, 256), (900, 70, 128)])
+def test_simple_mlp_matches_fp64(cuda, n, in_dim, hid):
+    import kgwas_b200
+    from kgwas_b200 import _lib
+    torch.manual_seed(n + in_dim)
+    mlp = kgwas_b200.SimpleMLP(in_dim, hid, hid)
+    ref = torch.nn.Sequential(torch.nn.Linear(in_dim, hid), torch.nn.ReLU(), torch.nn.Linear(hid, hid), torch.nn.ReLU(),
+                              torch.nn.Linear(hid, hid)).double()
+    with torch.no_grad():
+        for src, dst in ((mlp.FC_hidden, ref[0]), (mlp.FC_hidden2, ref[2]), (mlp.FC_output, ref[4])):
+            dst.weight.copy_(src.weight.double())
+            dst.bias.copy_(src.bias.double())
+    assert list(mlp.state_dict().keys()) == ["FC_hidden.weight", "FC_hidden.bias", "FC_hidden2.weight", "FC_hidden2.bias",
+                                             "FC_output.weight", "FC_output.bias"]
+    mlp = mlp.to(cuda)
+    x = torch.randn(n, in_dim)
+    up = torch.randn(n, hid)
+    xc = x.to(cuda).requires_grad_()
+    k0 = _lib.kernel_launch_count()
+    out = mlp(xc)
+    out.backward(up.to(cuda))
+    used_engine = _lib.kernel_launch_count() > k0
+    assert used_engine == (in_dim % 4 == 0)
+    xr = x.double().requires_grad_()
+    outr = ref(xr)
+    outr.backward(up.double())
+
+    def err(a, b):
+        return ((a.detach().cpu().double() - b.detach()).abs().max() / b.detach().abs().max()).item()
+    assert err(out, outr) < 2e-5
+    assert err(xc.grad, xr.grad) < 2e-5
+    for (a, b) in ((mlp.FC_hidden, ref[0]), (mlp.FC_hidden2, ref[2]), (mlp.FC_output, ref[4])):
+        assert err(a.weight.grad, b.weight.grad) < 5e-5
+        assert err(a.bias.grad, b.bias.grad) < 5e-5

@@ -63,6 +63,8 @@ def _run(backbone, cuda, logit_tol, grad_tol):
     assert err <= logit_tol, f"{backbone}: logits differ from the fp64 oracle by {err:.3e} of their scale"
     worst = 0.0
     n = 0
+    gscale = max(p.grad.abs().max().item() for p in ref.parameters()
+                 if not isinstance(p, torch.nn.parameter.UninitializedParameter) and p.grad is not None)
     for k, p in ref.named_parameters():
         if isinstance(p, torch.nn.parameter.UninitializedParameter):
             continue
@@ -70,10 +72,14 @@ def _run(backbone, cuda, logit_tol, grad_tol):
             assert k not in got_g, k
             continue
         assert k in got_g, k
-        e = (got_g[k].double() - p.grad).abs().max().item() / max(p.grad.abs().max().item(), 1e-30)
-        worst = max(worst, e)
+        own = max(p.grad.abs().max().item(), 1e-30)
+        e_abs = (got_g[k].double() - p.grad).abs().max().item()
+        worst = max(worst, e_abs / own)
+        # relative to the tensor's own scale, plus an absolute floor of 2e-5 of the largest gradient of the model: the
+        # gradient of a relation with few edges is tiny, and fp32 accumulation noise of the shared upstream sums does
+        # not shrink with it (same criterion as tests/test_oracle_golden.py)
         tol_k = max(grad_tol, 1e-2) if (".att_src" in k or ".att_dst" in k) else grad_tol
-        assert e <= tol_k, f"{backbone}: grad of {k} differs by {e:.3e}"
+        assert e_abs <= tol_k * own + 2e-5 * gscale, f"{backbone}: grad of {k} differs by {e_abs / own:.3e} of its scale"
         n += 1
     assert n >= 3 * 27
     e = (got_dx.double() - xr["Gene"].grad).abs().max().item() / xr["Gene"].grad.abs().max().item()
