@@ -373,6 +373,15 @@ k_gemm_tc_rows(const float* __restrict__ a, int64_t lda, const float* __restrict
   float* epi = reinterpret_cast<float*>(smem + 2 * B_TILE + STAGES_A * A_STAGE);
 
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  // blockIdx.y selects a 128-column slice of the output (N > 128: [nodes, h] x [h, R*h] products of the gene-sized
+  // jobs): the slice's part of B stays resident, the CTAs of one slice share the row tiles between them
+  {
+    const int64_t n_off = (int64_t)blockIdx.y * TN_;
+    b += LAYOUT == KGB_NT ? n_off * ldb : n_off;
+    c += n_off;
+    if (bias) bias += n_off;
+    N = min((int64_t)TN_, N - n_off);
+  }
   const int n_kb = (int)((K + BK - 1) / BK);
   const int64_t n_tiles = (M + TM - 1) / TM;
   const uint32_t bar0 = smem_u32(bars);
@@ -576,7 +585,12 @@ int gemm_tc(int layout, const float* a, int64_t lda, const float* b, int64_t ldb
     attr_set = true;
   }
   // node-row GEMMs with a resident [<=128, <=128] weight operand: persistent row-streaming kernel
-  if (layout != KGB_TN && N <= tc::TN_ && K <= tc::rs::KMAX && K % tc::BK == 0 && M >= 64 * 1024) {
+  // (also the gene-sized [nodes, h] x [h, R*h] products, one 128-column slice of the output per blockIdx.y: a tile
+  //  costs ~4.6 us here against ~20 us per CTA in the one-tile-per-CTA kernel below)
+  static const char* rs_env = getenv("KGB_GEMM_ROWS_MIN_M");
+  static const int64_t rs_min_m = rs_env ? atoll(rs_env) : 64 * 1024;   // measured: 4096 is neutral for the step (6.26 vs 6.23 ms)
+  if (layout != KGB_TN && (N <= tc::TN_ || N % tc::TN_ == 0) && N <= 8 * tc::TN_ && K <= tc::rs::KMAX && K % tc::BK == 0 &&
+      (M >= 64 * 1024 || (M >= rs_min_m && N >= tc::TN_))) {
     static bool rs_attr = false;
     if (!rs_attr) {
       KGB_CUDA_OK(cudaFuncSetAttribute(tc::rs::k_gemm_tc_rows<KGB_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::rs::SMEM));
@@ -584,7 +598,11 @@ int gemm_tc(int layout, const float* a, int64_t lda, const float* b, int64_t ldb
       rs_attr = true;
     }
     const int64_t tiles = (M + tc::TM - 1) / tc::TM;
-    const unsigned g = (unsigned)(tiles < kNumSMs ? tiles : kNumSMs);
+    const int64_t slices = (N + tc::TN_ - 1) / tc::TN_;
+    int64_t gx = kNumSMs / slices;                       // one wave of CTAs: one CTA per SM (218 KB of shared memory)
+    if (gx < 1) gx = 1;
+    if (gx > tiles) gx = tiles;
+    const dim3 g((unsigned)gx, (unsigned)slices, 1);
     if (layout == KGB_NT)
       tc::rs::k_gemm_tc_rows<KGB_NT><<<g, tc::rs::THREADS_RS, tc::rs::SMEM, stream>>>(a, lda, b, ldb, c, ldc, M, N, K, alpha, beta, bias, relu);
     else

@@ -37,7 +37,8 @@ def test_tc_nt(cuda, m, n, k):
     assert _err(c2, ref2, k) < TOL
 
 
-@pytest.mark.parametrize("m,n,k", [(4096, 128, 128), (20371, 768, 128), (20371, 128, 768), (1001, 640, 128), (784256, 128, 128)])
+@pytest.mark.parametrize("m,n,k", [(4096, 128, 128), (20371, 768, 128), (20371, 128, 768), (1001, 640, 128), (784256, 128, 128),
+                                   (2037, 5120, 128), (2037, 1024, 128), (2037, 2048, 64)])
 def test_tc_nn(cuda, m, n, k):
     from kgwas_b200 import _lib
     torch.manual_seed(m + n)
@@ -102,7 +103,8 @@ def test_tc_accuracy_is_fp32_class(cuda):
 
 
 @pytest.mark.parametrize("layout", ["NT", "NN"])
-@pytest.mark.parametrize("m,n,k", [(784256, 128, 128), (70001, 128, 128), (100000, 64, 64), (65536, 32, 128), (300000, 128, 32)])
+@pytest.mark.parametrize("m,n,k", [(784256, 128, 128), (70001, 128, 128), (100000, 64, 64), (65536, 32, 128), (300000, 128, 32),
+                                   (70001, 256, 128), (66000, 768, 64)])
 def test_tc_row_streaming_kernel(cuda, layout, m, n, k):
     """Persistent node-row GEMM (resident weights, two TMEM accumulator sets): ragged last tile, narrow N / K,
     epilogue options, and repeatability."""
