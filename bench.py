@@ -382,7 +382,7 @@ class Runner:
             ref_g = dict(ref_model.named_parameters())
             gscale = max(float(p.grad.abs().max()) for p in ref_g.values()
                          if not isinstance(p, torch.nn.parameter.UninitializedParameter) and p.grad is not None)
-            gerr, n_g, n_none_vs_zero = 0.0, 0, 0
+            gerr, n_g, n_none_vs_zero, bad_keys = 0.0, 0, 0, []
             for k, p in params:
                 rg = ref_g[k].grad
                 if rg is None and p.grad is None:
@@ -395,11 +395,12 @@ class Runner:
                     other = rg if rg is not None else p.grad
                     if float(other.abs().max()) != 0.0:
                         gerr = float("inf")
+                        bad_keys.append(k)
                     n_none_vs_zero += 1
                     continue
                 gerr = max(gerr, float((p.grad - rg).abs().max()) / max(gscale, 1e-30))
                 n_g += 1
-            res = {"err": err, "grad_err": gerr, "tolerance": 1e-4, "n_logits": int(pf.numel()), "n_grad_tensors": n_g, "n_grads_none_vs_zero": n_none_vs_zero,
+            res = {"err": err, "grad_err": gerr, "tolerance": 1e-4, "n_logits": int(pf.numel()), "n_grad_tensors": n_g, "n_grads_none_vs_zero": n_none_vs_zero, "grads_missing_on_one_side": bad_keys[:5],
                    "loss_sharded": float(loss_all.item()), "loss_unsharded": float(lf.item()),
                    "against": "the same KG and weights run un-sharded on rank 0 (forward + backward), all per-SNP logits"}
             del ref_model, fd, xf, pf, lf

@@ -207,8 +207,8 @@ def _hetero_sage(convs: Dict[EdgeType, SAGEConv], x_dict, edge_index_dict, aggr:
                                    *[c.lin_l.bias for c in cs], *[c.lin_r.weight for c in cs],
                                    *([head[1]] if head is not None else []))
     out = dict(zip(plan.dst_types, outs))
-    if shard is not None:
-        out = shard.combine(out, relu)     # sum the partial rows of shared node types across ranks, then ReLU
+    # (sharded runs: the layer Function itself sums the partial rows of the shared node types across ranks and applies
+    #  their ReLU -- an all-reduce per shared type on a side stream, overlapping the SNP-row kernels; see ops.py)
     if head is not None:
         out[("head", head[0])] = outs[-1]
     return out

@@ -221,6 +221,10 @@ class _SageLayerCtx:
         # adds the root term (and bias) only for rows [lo, hi); the partial outputs are summed across ranks and
         # the ReLU runs after that sum, outside this Function.
         self.root_range = root_range or {}
+        # the cross-rank sum of a shared type's partial rows (forward) / of its masked gradient (backward) is issued by
+        # the layer itself, as one more recorded launch on a side stream, so that it overlaps the SNP-row kernels of the
+        # same pass instead of sitting between two layers
+        self.exchange = bool(self.root_range)
 
     def fused_relu(self, T: str) -> bool:
         return self.relu and T not in self.root_range
@@ -323,6 +327,13 @@ class HeteroSageLayerFn(torch.autograd.Function):
                     saved_A[(T, ji)] = buf
             if T == head_T and not head_in_spmm:
                 sch.run(big_T, P(_lib.rowdot, out, w_head, pred, h, 1, 0), (out, w_head), (pred,), "fwd head", T)
+            if meta.exchange and T in meta.root_range:
+                def exchange(out=out, relu=meta.relu):
+                    import torch.distributed as dist
+                    dist.all_reduce(out, op=dist.ReduceOp.SUM)      # partial rows of every rank -> the full rows
+                    if relu:
+                        out.relu_()
+                sch.run(False, exchange, (out,), (out,), f"fwd all-reduce {T}", ("comm", T))
         outs = [prep[T][0] for T in plan.dst_types]
         sch.keep.append(prep)
         sch.join()
@@ -397,6 +408,20 @@ class HeteroSageLayerFn(torch.autograd.Function):
                         (dy, outs[T], dpc, w_head), (g, sums), f"bwd relu {T}", T)
                 if dp is not None:
                     d_w_head = sums[1:2]
+            elif meta.exchange and T in meta.root_range:
+                # d_out is this rank's gradient w.r.t. the (ReLU-ed) SUM over ranks: mask it, sum it over ranks -- every
+                # rank's partial rows entered that sum with weight one -- and only then use it
+                g = _empty(n_t, h, Wl)
+                dy = d_out.contiguous()
+
+                def exchange_bwd(g=g, dy=dy, y=outs[T], relu=meta.relu, scale=scale):
+                    import torch.distributed as dist
+                    if relu:
+                        _lib.relu_bwd_fused(g, h, dy=dy, y=y, scale=scale)
+                    else:
+                        torch.mul(dy, scale, out=g)
+                    dist.all_reduce(g, op=dist.ReduceOp.SUM)
+                sch.run(False, exchange_bwd, (dy, outs[T]), (g,), f"bwd all-reduce {T}", ("comm", T))
             else:
                 g = d_out.contiguous()
                 if scale != 1.0:
