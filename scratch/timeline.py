@@ -15,12 +15,18 @@ def main():
     layers = int(sys.argv[3]) if len(sys.argv) > 3 else 2
     sys.argv = [sys.argv[0]]
     args = bench.parse()
-    dev = torch.device("cuda:0")
-    torch.cuda.set_device(0)
-    r = bench.Runner(args, dev, 0, 1, "single", backbone=backbone, hidden=hidden, layers=layers)
+    world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    if world > 1:
+        import datetime
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=120))
+        args.no_parity = True
+    r = bench.Runner(args, dev, rank, world, "single" if world == 1 else "strong", backbone=backbone, hidden=hidden, layers=layers)
     r.prepare()
     ms, _ = r.time_resident(10)
-    print(f"{backbone} h={hidden} L={layers}: {ms:.3f} ms/step ({r.graph_note})")
+    print(f"{backbone} h={hidden} L={layers} world={world}: {ms:.3f} ms/step ({r.graph_note})")
     from torch.profiler import ProfilerActivity, profile
     with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
         for _ in range(3):
@@ -37,7 +43,11 @@ def main():
     last = [e for e in evs if e.time_range.start >= t_end - step_us * 1.02]
     t0 = min(e.time_range.start for e in last)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    path = os.path.join(ROOT, "gpurun_out", f"timeline_{backbone}_h{hidden}_L{layers}.csv")
+    if rank != 0:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+        return
+    path = os.path.join(ROOT, "gpurun_out", f"timeline_{backbone}_h{hidden}_L{layers}" + (f"_n{world}" if world > 1 else "") + ".csv")
     streams = {}
     with open(path, "w") as f:
         f.write("start_us,dur_us,stream,name\n")
@@ -70,6 +80,10 @@ def main():
         names = [f"{x.name[:40]}({x.time_range.end - x.time_range.start:.0f})" for x in last
                  if x.time_range.start - t0 < b and x.time_range.end - t0 > a and x.time_range.end - x.time_range.start < 100]
         print(f"  gap {a:.0f}-{b:.0f} us ({b - a:.0f}): " + ", ".join(names[:14]))
+    if world > 1:
+        torch.distributed.barrier()
+        r.close()
+        torch.distributed.destroy_process_group()
 
 
 if __name__ == "__main__":

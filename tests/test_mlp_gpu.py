@@ -23,6 +23,17 @@ def test_simple_mlp_matches_fp64(cuda, n, in_dim, hid):
                                              "FC_output.weight", "FC_output.bias"]
     mlp = mlp.to(cuda)
     x = torch.randn(n, in_dim)
+    # keep every hidden pre-activation away from the ReLU kink: an element within fp32 rounding of 0 may fall on the other
+    # side in fp32 than in fp64 and then moves a whole gradient row by O(1e-3) -- a property of ReLU, not of the kernels
+    for _ in range(50):
+        with torch.no_grad():
+            p1 = ref[0](x.double())
+            p2 = ref[2](p1.relu())
+        bad = ((p1.abs() < 1e-3).any(1) | (p2.abs() < 1e-3).any(1)).nonzero().reshape(-1)
+        if bad.numel() == 0:
+            break
+        x[bad] = torch.randn(bad.numel(), in_dim)
+    assert bad.numel() == 0
     up = torch.randn(n, hid)
     xc = x.to(cuda).requires_grad_()
     k0 = _lib.kernel_launch_count()
@@ -38,10 +49,7 @@ def test_simple_mlp_matches_fp64(cuda, n, in_dim, hid):
         return ((a.detach().cpu().double() - b.detach()).abs().max() / b.detach().abs().max()).item()
     # fp32-class accuracy (3xTF32 products, fp32 accumulation; K up to 5120): an order below north_star's 1e-4
     assert err(out, outr) < 2e-5, err(out, outr)
-    # d x: a hidden pre-activation within fp32 rounding of 0 (about one in 10^6 at K = 5120) may fall on the other side
-    # of the ReLU kink than in fp64 and moves ONE row of d x by O(1e-3): every row but at most two must be fp32-exact
-    row_err = (xc.grad.detach().cpu().double() - xr.grad).abs().max(1).values / xr.grad.abs().max()
-    assert int((row_err > 1e-4).sum()) <= 2 and float(row_err.max()) < 2e-2, (int((row_err > 1e-4).sum()), float(row_err.max()))
+    assert err(xc.grad, xr.grad) < 1e-4, err(xc.grad, xr.grad)
     for (a, b) in ((mlp.FC_hidden, ref[0]), (mlp.FC_hidden2, ref[2]), (mlp.FC_output, ref[4])):
         assert err(a.weight.grad, b.weight.grad) < 1e-4, err(a.weight.grad, b.weight.grad)
         assert err(a.bias.grad, b.bias.grad) < 1e-4, err(a.bias.grad, b.bias.grad)
