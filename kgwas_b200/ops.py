@@ -32,7 +32,7 @@ CHAIN_PRIORITY = __import__("os").environ.get("KGB_CHAIN_PRIORITY") == "1"   # i
 TRACE = None             # scratch/trace_step.py sets this to a list: (label, stream name, start event, end event) per launch
 
 
-def issue_order(ops):
+def issue_order(ops, chain_priority=None):
     """Pure scheduling logic of ``_Sched.join`` (unit-tested on CPU).
 
     ``ops``: program-ordered list of ``(big, read_keys, write_keys)``.  Returns ``(preds, succs, order)``: the
@@ -82,7 +82,7 @@ def issue_order(ops):
         tail[i] = (10 if ops[i][0] else 1) + max((tail[j] for j in succs[i]), default=0)
         desc[i] = sum(1 + desc[j] for j in succs[i])
     indeg = [len(preds[i]) for i in range(n)]
-    if not CHAIN_PRIORITY:
+    if not (CHAIN_PRIORITY if chain_priority is None else chain_priority):
         tail = desc = [0] * n
     heap = [(cls[i], -tail[i], -desc[i], i) for i in range(n) if indeg[i] == 0]
     heapq.heapify(heap)
@@ -119,8 +119,9 @@ class _Sched:
 
     N_SMALL = 3
 
-    def __init__(self, device):
+    def __init__(self, device, chain_priority=None):
         self.device = device
+        self.chain_priority = chain_priority
         on_gpu = device.type == "cuda"     # (CPU tensors never reach a kernel: _lib raises; tests stub _lib)
         self.main = torch.cuda.current_stream(device) if on_gpu else None
         self.ops = []          # (big, fn, read keys, write keys, label, chain)
@@ -153,12 +154,12 @@ class _Sched:
             self.keep.clear()
             return
         if not self.smalls:                                   # single stream: program order
-            seq = issue_order([(o[0], o[2], o[3]) for o in ops])[2] if ISSUE_ORDER_ALWAYS else range(n)
+            seq = issue_order([(o[0], o[2], o[3]) for o in ops], self.chain_priority)[2] if ISSUE_ORDER_ALWAYS else range(n)
             for i in seq:
                 self._launch(ops[i][1], self.main, ops[i][4], True)
             self.keep.clear()
             return
-        preds, succs, order = issue_order([(o[0], o[2], o[3]) for o in ops])
+        preds, succs, order = issue_order([(o[0], o[2], o[3]) for o in ops], self.chain_priority)
         chains, ev_of, st_of = {}, [None] * n, [None] * n
         start = _event_from_pool(self, 0)
         start.record(self.main)
@@ -280,7 +281,9 @@ class HeteroSageLayerFn(torch.autograd.Function):
                 pred = _empty(n_t, 1, Wl)
         # ---- phase 2: record every launch with the scheduler (nothing runs yet), then let it issue them: big kernels
         # back to back on this stream, small chains on high-priority side streams, ordered by the data they touch ----
-        sch = _Sched(Wl.device)
+        # sharded runs: the gather with a cross-rank sum behind it goes first (measured at N = 2: 4.27 -> 4.16 ms/step; on one
+        # GPU the same order only moves the contention, 6.22 -> 6.37 ms)
+        sch = _Sched(Wl.device, chain_priority=True if meta.exchange else None)
         P = functools.partial
         for T in sorted(plan.dst_types, key=lambda t: -plan.num_nodes[t]):
             scale = meta.rel_scale[T]
@@ -383,7 +386,7 @@ class HeteroSageLayerFn(torch.autograd.Function):
         # Largest destination type first: its dense d x = g . W_root then is the first (overwriting) writer.  Launches
         # are only recorded here; placement (SNP-sized kernels on this stream, everything else on high-priority side
         # streams), issue order and cross-stream ordering are the scheduler's.
-        sch = _Sched(Wl.device)
+        sch = _Sched(Wl.device, chain_priority=True if meta.exchange else None)
         P = functools.partial
         order = sorted(range(len(plan.dst_types)), key=lambda i: -plan.num_nodes[plan.dst_types[i]])
         late = []       # recorded after everything else: small consumers of a big gather-reduce (see below)

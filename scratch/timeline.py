@@ -44,6 +44,7 @@ def main():
     t0 = min(e.time_range.start for e in last)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     if rank != 0:
+        r.close()
         torch.distributed.barrier()
         torch.distributed.destroy_process_group()
         return
@@ -81,8 +82,8 @@ def main():
                  if x.time_range.start - t0 < b and x.time_range.end - t0 > a and x.time_range.end - x.time_range.start < 100]
         print(f"  gap {a:.0f}-{b:.0f} us ({b - a:.0f}): " + ", ".join(names[:14]))
     if world > 1:
-        torch.distributed.barrier()
         r.close()
+        torch.distributed.barrier()
         torch.distributed.destroy_process_group()
 
 
