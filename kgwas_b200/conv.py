@@ -20,6 +20,7 @@ from .ops import HeteroSageLayerFn, _SageLayerCtx
 from .plan import get_plan
 
 EdgeType = Tuple[str, str, str]
+MERGE_XF = __import__("os").environ.get("KGB_MERGE_XF", "1") == "1"   # one multi-source gather-reduce per destination type
 
 
 def glorot_(t: Tensor) -> Tensor:
@@ -180,9 +181,9 @@ def _hetero_sage(convs: Dict[EdgeType, SAGEConv], x_dict, edge_index_dict, aggr:
     num_nodes = {t: int(x.size(0)) for t, x in x_dict.items()}
     if shard is not None:
         with shard.building_plan():
-            plan = get_plan(edge_index_dict, num_nodes, frozenset(convs.keys()))
+            plan = get_plan(edge_index_dict, num_nodes, frozenset(convs.keys()), merge_xf=MERGE_XF)
     else:
-        plan = get_plan(edge_index_dict, num_nodes, frozenset(convs.keys()))
+        plan = get_plan(edge_index_dict, num_nodes, frozenset(convs.keys()), merge_xf=MERGE_XF)
     if not plan.rel_order:
         return {}
     h = convs[plan.rel_order[0]].out_channels

@@ -270,8 +270,11 @@ class HeteroSageLayerFn(torch.autograd.Function):
                 bias = bias * scale
             job_bufs = []
             for job in plan.jobs[T]:
-                lo, hi = job.rel_ids[0], job.rel_ids[-1] + 1
                 job.schedule(h)
+                if getattr(job, "multi", False):               # one Z table for several source types
+                    job_bufs.append((None, _empty(job.total_rows, h, Wl)))
+                    continue
+                lo, hi = job.rel_ids[0], job.rel_ids[-1] + 1
                 if job.mode == "xf":       # Z = X_src . [W_1;..;W_R]^T  (view: rows k*h.. = W_l^k)
                     job_bufs.append((Wl[lo:hi].reshape(job.R * h, h), _empty(job.n_src, job.R * h, Wl)))
                 else:                      # A = gather-reduce, then out += A . [W_1|..|W_R]^T
@@ -308,10 +311,23 @@ class HeteroSageLayerFn(torch.autograd.Function):
                 sch.run(big_T, P(_lib.gemm, KGB_NT, x[T], w_root, out, n_t, h, h, alpha=scale, bias=bias,
                                  relu=relu_T and not jobs), (x[T], w_root, bias), (out,), f"fwd root {T}", T)
             for ji, job in enumerate(jobs):
-                R, xs_ = job.R, x[job.src_type]
                 last_relu = relu_T and ji == len(jobs) - 1
                 w_job, buf = job_bufs[ji]
                 big_e = job.n_edges >= BIG_EDGES
+                if getattr(job, "multi", False):
+                    for (S, R_i, lo_i, hi_i, n_i, off) in job.parts:
+                        w_i = Wl[lo_i:hi_i].reshape(R_i * h, h)
+                        z_i = buf[off:off + n_i * R_i].view(n_i, R_i * h)
+                        sch.run(False, P(_lib.gemm, KGB_NT, x[S], w_i, z_i, n_i, R_i * h, h, alpha=scale), (x[S], w_i), (buf,),
+                                f"fwd Z {S}->{T}", T)
+                        sch.keep.append(w_i)
+                    hd = head_in_spmm and ji == len(jobs) - 1
+                    sch.run(big_T or big_e,
+                            P(_lib.spmm, job.csr, buf, out, h, ew=job.w_mean, beta=1.0, relu=last_relu,
+                              dot_w=w_head if hd else None, dot_out=pred if hd else None),
+                            (buf, out, w_head if hd else None), (out, pred if hd else None), f"fwd spmm xf {job.src_type}->{T}", T)
+                    continue
+                R, xs_ = job.R, x[job.src_type]
                 if job.mode == "xf":
                     sch.run(job.n_src >= BIG_ROWS, P(_lib.gemm, KGB_NT, xs_, w_job, buf, job.n_src, R * h, h, alpha=scale),
                             (xs_, w_job), (buf,), f"fwd Z {job.src_type}->{T}", T)
@@ -459,10 +475,25 @@ class HeteroSageLayerFn(torch.autograd.Function):
                     _lib.gemm(KGB_NN, gr, w_root, o, m, h, h, beta=beta)
                 sch.run(big_T, root_dx, (g, w_root, buf), (buf,), f"bwd dx root {T}", T)
             for ji, job in enumerate(plan.jobs[T]):
+                big_e = job.n_edges >= BIG_EDGES
+                if getattr(job, "multi", False):
+                    dz = _empty(job.total_rows, h, g)
+                    sch.run(big_T or big_e, P(_lib.spmm, job.tcsr, g, dz, h, ew=job.w_mean_t), (g,), (dz,),
+                            f"bwd spmm xf {T}->{job.src_type}", T)
+                    for (S, R_i, lo_i, hi_i, n_i, off) in job.parts:
+                        dz_i = dz[off:off + n_i * R_i].view(n_i, R_i * h)
+                        if need_w:
+                            sch.run(False, P(_lib.gemm, KGB_TN, dz_i, x[S], dWl[lo_i:hi_i].view(R_i * h, h), R_i * h, h, n_i),
+                                    (dz, x[S]), (dWl,), f"bwd dWl xf {T}->{S}", T)
+                        if need_x[S]:
+                            buf, beta = dx_target(S)
+                            w_nn = Wl[lo_i:hi_i].reshape(R_i * h, h)
+                            sch.run(False, P(_lib.gemm, KGB_NN, dz_i, w_nn, buf, n_i, h, R_i * h, beta=beta), (dz, w_nn, buf),
+                                    (buf,), f"bwd dx xf {T}->{S}", T)
+                    continue
                 lo, hi = job.rel_ids[0], job.rel_ids[-1] + 1
                 R, S = job.R, job.src_type
                 big_S = plan.num_nodes[S] >= BIG_ROWS
-                big_e = job.n_edges >= BIG_EDGES
                 if job.mode == "xf":
                     dz = _empty(job.n_src, R * h, g)
                     sch.run(big_T or big_e, P(_lib.spmm, job.tcsr, g, dz.view(job.n_src * R, h), h, ew=job.w_mean_t),

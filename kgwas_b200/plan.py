@@ -49,8 +49,10 @@ class PairJob:
         dst = torch.cat([ei[1] for ei in edge_indices])
         slot = torch.cat([torch.full((s,), k, dtype=torch.int64, device=dev) for k, s in enumerate(sizes)])
         group = dst * R + slot                                   # softmax / mean group of every edge
+        self._coo = None
         if self.mode == "xf":
             job_src, job_dst, n_js, n_jd = src * R + slot, dst, n_src * R, n_dst
+            self._coo = (job_src, dst, slot)   # kept for LayerPlan(merge_xf=True): MultiXfJob re-bases the table rows
             presort = slot * n_src + src       # slots of a row ordered by (relation slot, source): groups stay contiguous
         else:
             job_src, job_dst, n_js, n_jd = src, group, n_src, n_dst * R
@@ -131,11 +133,66 @@ class PairJob:
                 f"heavy_rows={self.csr.n_hrows}/{self.tcsr.n_hrows})")
 
 
+class MultiXfJob:
+    """Several transform-first pair jobs into ONE destination type merged into one gather-reduce (SAGE only).
+
+    The destination rows of e.g. ``Gene`` are fed by Gene->Gene, BP->Gene, MF->Gene and CC->Gene relations; as separate jobs
+    they form a chain of dependent gene-sized launches (Z GEMM, gather-reduce, Z GEMM, gather-reduce, ...) that every
+    rank of a sharded run repeats and that the SNP-row kernels have to share the SMs with.  Here the ``Z`` products of all
+    sources are written into ONE table (part i owns rows ``[row_off_i, row_off_i + n_src_i * R_i)``, viewed as
+    ``[n_src_i, R_i * h]``) and ONE CSR over the destination rows gathers from it: chain depth 2 instead of 2 per source
+    type.  Mean weights are per (destination, relation), exactly as in the separate jobs."""
+
+    mode = "xf"
+    multi = True
+
+    def __init__(self, dst_type: str, parts: List["PairJob"], n_dst: int):
+        self.dst_type, self.n_dst = dst_type, n_dst
+        self.parts = []                     # (src_type, R, lo, hi, n_src, row_off)
+        dev = parts[0].csr.col.device
+        srcs, dsts, groups = [], [], []
+        row_off, slot_base = 0, 0
+        r_tot = sum(p.R for p in parts)
+        for p in parts:
+            self.parts.append((p.src_type, p.R, p.rel_ids[0], p.rel_ids[-1] + 1, p.n_src, row_off))
+            src_rows, dst, slot = p._coo                       # table row s*R+k inside the part, destination, slot k
+            srcs.append(src_rows + row_off)
+            dsts.append(dst)
+            groups.append(dst * r_tot + slot_base + slot)
+            row_off += p.n_src * p.R
+            slot_base += p.R
+        self.total_rows = row_off
+        self.n_edges = sum(p.n_edges for p in parts)
+        job_src, job_dst, group = torch.cat(srcs), torch.cat(dsts), torch.cat(groups)
+        self.csr, self.eperm, self.tcsr, self.t_eperm = _lib.csr_build(job_src, job_dst, self.total_rows, n_dst, sort_cols=True)
+        deg = torch.bincount(group, minlength=n_dst * r_tot)
+        if DEG_REDUCE is not None:
+            deg = DEG_REDUCE(deg, dst_type)
+        w = (1.0 / deg.clamp(min=1).to(torch.float32))[group]
+        self.w_mean = w[self.eperm.long()].contiguous()
+        self.w_mean_t = self.w_mean[self.t_eperm.long()].contiguous()
+        self.src_type = "+".join(p[0] for p in self.parts)
+        self.n_src = max(p[4] for p in self.parts)
+        self.rels = [et for p in parts for et in p.rels]
+        self._scheduled_h = None
+
+    def schedule(self, h: int):
+        if self._scheduled_h != h:
+            self.csr.schedule_for_l2(4 * h)
+            self.tcsr.schedule_for_l2(4 * h)
+            self._scheduled_h = h
+        return self
+
+    def __repr__(self):
+        return f"MultiXfJob({self.src_type}->{self.dst_type}, parts={len(self.parts)}, E={self.n_edges})"
+
+
 class LayerPlan:
     """All jobs of one ``edge_index_dict``; shared by every layer of the model."""
 
     def __init__(self, edge_index_dict: Dict[EdgeType, torch.Tensor], num_nodes: Dict[str, int],
-                 conv_keys=None):
+                 conv_keys=None, merge_xf: bool = False):
+        self.merge_xf = merge_xf
         self.edge_types: List[EdgeType] = [et for et in edge_index_dict
                                            if (conv_keys is None or et in conv_keys)
                                            and et[0] in num_nodes and et[2] in num_nodes]
@@ -171,11 +228,25 @@ class LayerPlan:
             # set (SNP -> Gene) ends with a small GEMM that has to wait for its big gather-reduce: put such jobs LAST,
             # so that the small jobs of this destination type are not chained behind a big kernel (ops._Sched).
             self.jobs[T].sort(key=lambda j: j.mode == "af" and (j.n_edges >= BIG_EDGES or j.n_src >= BIG_ROWS))
+            if merge_xf:
+                # the small transform-first jobs of this destination type become one gather-reduce over one Z table
+                small = [j for j in self.jobs[T] if j.mode == "xf" and j.n_edges < BIG_EDGES and j.n_src < BIG_ROWS]
+                if len(small) >= 2:
+                    merged = MultiXfJob(T, small, num_nodes[T])
+                    first = self.jobs[T].index(small[0])
+                    rest = [j for j in self.jobs[T] if j not in small]
+                    self.jobs[T] = rest[:first] + [merged] + rest[first:]
+        for js in self.jobs.values():
+            for j in js:
+                if getattr(j, "_coo", None) is not None:
+                    j._coo = None                                  # the COO copies were only needed for merging
         self.n_edges = sum(j.n_edges for js in self.jobs.values() for j in js)
         self._tensors = [edge_index_dict[et] for et in self.edge_types]   # identity anchors for the cache
         self._versions = [t._version for t in self._tensors]
 
-    def matches(self, edge_index_dict, num_nodes, conv_keys) -> bool:
+    def matches(self, edge_index_dict, num_nodes, conv_keys, merge_xf=False) -> bool:
+        if merge_xf != self.merge_xf:
+            return False
         ets = [et for et in edge_index_dict if (conv_keys is None or et in conv_keys)
                and et[0] in num_nodes and et[2] in num_nodes]
         if ets != self.edge_types or num_nodes != self.num_nodes:
@@ -185,22 +256,23 @@ class LayerPlan:
 
 
 _CACHE: List[LayerPlan] = []
-_CACHE_SIZE = 2
+_CACHE_SIZE = 4
 plan_builds = 0
 
 
-def get_plan(edge_index_dict, num_nodes: Dict[str, int], conv_keys=None) -> LayerPlan:
-    """Plans are cached on tensor identity (+ in-place version), most recent first."""
+def get_plan(edge_index_dict, num_nodes: Dict[str, int], conv_keys=None, merge_xf: bool = False) -> LayerPlan:
+    """Plans are cached on tensor identity (+ in-place version), most recent first.  ``merge_xf``: the SAGE layer's
+    variant with one multi-source gather-reduce per destination type (``MultiXfJob``)."""
     global plan_builds
     for i, p in enumerate(_CACHE):
-        if p.matches(edge_index_dict, num_nodes, conv_keys):
+        if p.matches(edge_index_dict, num_nodes, conv_keys, merge_xf):
             if i:
                 _CACHE.insert(0, _CACHE.pop(i))
             return p
     for et, ei in edge_index_dict.items():
         if ei.dtype != torch.int64 or ei.dim() != 2 or ei.size(0) != 2:
             raise ValueError(f"edge_index of {et} must be int64 [2, E], got {ei.dtype} {tuple(ei.shape)}")
-    p = LayerPlan(edge_index_dict, num_nodes, conv_keys)
+    p = LayerPlan(edge_index_dict, num_nodes, conv_keys, merge_xf)
     plan_builds += 1
     _CACHE.insert(0, p)
     del _CACHE[_CACHE_SIZE:]
