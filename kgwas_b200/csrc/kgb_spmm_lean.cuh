@@ -1,6 +1,6 @@
 // Instruction-lean segmented gather-reduce (the SAGE mean / sum aggregation and its backward).
 //
-// ncu on the generic kernel (profiles/r01_ncu_spmm_v0_v1.md): 32 warp instructions per edge, issue slots 45 % busy and
+// ncu on the generic kernel (profiles/r01_spmm_variants.md, profiles/r01_ncu_spmm_step.md): 32 warp instructions per edge, issue slots 45 % busy and
 // every row paying five to seven dependent memory round trips -- the kernel is bound by instruction issue AND exposed
 // latency long before L2 (38 %) or HBM.  This version
 //   * spends ~7 instructions per edge: one SHFL for the column, one for the weight, one IMAD.WIDE for the row address,
