@@ -1,5 +1,5 @@
-"""ncu raw page (csv) of every kgb_spmm launch of ONE bench step -> profiles/r01_spmm_traffic.json (+ a table on stdout).
-usage: ncu -i rep.ncu-rep --page raw --csv > raw.csv ; python scratch/ncu_traffic.py raw.csv "<source note>" """
+"""ncu raw page (csv) of every kgb_spmm launch of ONE bench step -> profiles/<out>.json (+ a table on stdout).
+usage: ncu -i rep.ncu-rep --page raw --csv > raw.csv ; python scratch/ncu_traffic.py raw.csv "<source note>" [out.json] """
 import csv
 import json
 import os
@@ -30,5 +30,5 @@ for k, d in enumerate(data):
           f"{float(d[ix['smsp__issue_active.avg.pct_of_peak_sustained_active']]):.1f} |")
 out = {"hidden": 128, "backbone": "SAGE", "launches": len(data), "dram_bytes_per_step": tot,
        "source": sys.argv[2] if len(sys.argv) > 2 else "ncu --set full, one bench step"}
-json.dump(out, open(os.path.join(ROOT, "profiles", "r01_spmm_traffic.json"), "w"), indent=1)
+json.dump(out, open(os.path.join(ROOT, "profiles", sys.argv[3] if len(sys.argv) > 3 else "r02_spmm_traffic.json"), "w"), indent=1)
 print(f"\ntotal DRAM bytes of {len(data)} launches: {tot / 1e9:.3f} GB")
