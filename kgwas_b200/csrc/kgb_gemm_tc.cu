@@ -355,12 +355,12 @@ constexpr int EPI_COLS = 32;                              // epilogue transposes
 constexpr int EPI_LD2 = EPI_COLS + 4;
 constexpr int EPI_WARP = 32 * EPI_LD2 * 4;
 constexpr int SMEM = 2 * B_TILE + STAGES_A * A_STAGE + 4 * EPI_WARP + 256;
-constexpr int PROD_WARPS = 8;                             // 8 x 8 KB of A in flight per SM
-constexpr int THREADS_RS = (PROD_WARPS + 1 + 4) * 32;     // producers, MMA issuer, epilogue
+// PROD_WARPS (template parameter PW) x 8 KB of A in flight per SM; threads = producers, MMA issuer, 4 epilogue warps
+constexpr int threads_rs(int pw) { return (pw + 1 + 4) * 32; }
 static_assert(SMEM <= 227 * 1024, "row-streaming GEMM smem budget");
 
-template <int LAYOUT>   // KGB_NT: B[N,K] k-contiguous; KGB_NN: B[K,N] row-contiguous
-__global__ void __launch_bounds__(THREADS_RS, 1)
+template <int LAYOUT, int PROD_WARPS>   // KGB_NT: B[N,K] k-contiguous; KGB_NN: B[K,N] row-contiguous; PROD_WARPS must be 2 * STAGES_A
+__global__ void __launch_bounds__(threads_rs(PROD_WARPS), 1)
 k_gemm_tc_rows(const float* __restrict__ a, int64_t lda, const float* __restrict__ b, int64_t ldb, float* __restrict__ c,
                int64_t ldc, int64_t M, int64_t N, int64_t K, float alpha, float beta, const float* __restrict__ bias,
                int relu) {
@@ -591,10 +591,12 @@ int gemm_tc(int layout, const float* a, int64_t lda, const float* b, int64_t ldb
   static const int64_t rs_min_m = rs_env ? atoll(rs_env) : 64 * 1024;   // measured: 4096 is neutral for the step (6.26 vs 6.23 ms)
   if (layout != KGB_TN && (N <= tc::TN_ || N % tc::TN_ == 0) && N <= 8 * tc::TN_ && K <= tc::rs::KMAX && K % tc::BK == 0 &&
       (M >= 64 * 1024 || (M >= rs_min_m && N >= tc::TN_))) {
+    // (8 producer warps: two per stage of the 4-stage ring, which is what the phase bookkeeping of the producers assumes;
+    //  12 warps -- three per stage -- deadlock, measured in round 2)
     static bool rs_attr = false;
     if (!rs_attr) {
-      KGB_CUDA_OK(cudaFuncSetAttribute(tc::rs::k_gemm_tc_rows<KGB_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::rs::SMEM));
-      KGB_CUDA_OK(cudaFuncSetAttribute(tc::rs::k_gemm_tc_rows<KGB_NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::rs::SMEM));
+      KGB_CUDA_OK(cudaFuncSetAttribute(tc::rs::k_gemm_tc_rows<KGB_NT, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::rs::SMEM));
+      KGB_CUDA_OK(cudaFuncSetAttribute(tc::rs::k_gemm_tc_rows<KGB_NN, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::rs::SMEM));
       rs_attr = true;
     }
     const int64_t tiles = (M + tc::TM - 1) / tc::TM;
@@ -603,10 +605,10 @@ int gemm_tc(int layout, const float* a, int64_t lda, const float* b, int64_t ldb
     if (gx < 1) gx = 1;
     if (gx > tiles) gx = tiles;
     const dim3 g((unsigned)gx, (unsigned)slices, 1);
-    if (layout == KGB_NT)
-      tc::rs::k_gemm_tc_rows<KGB_NT><<<g, tc::rs::THREADS_RS, tc::rs::SMEM, stream>>>(a, lda, b, ldb, c, ldc, M, N, K, alpha, beta, bias, relu);
-    else
-      tc::rs::k_gemm_tc_rows<KGB_NN><<<g, tc::rs::THREADS_RS, tc::rs::SMEM, stream>>>(a, lda, b, ldb, c, ldc, M, N, K, alpha, beta, bias, relu);
+#define KGB_ROWS(LAY, PW) tc::rs::k_gemm_tc_rows<LAY, PW><<<g, tc::rs::threads_rs(PW), tc::rs::SMEM, stream>>>(a, lda, b, ldb, c, ldc, M, N, K, alpha, beta, bias, relu)
+    if (layout == KGB_NT) KGB_ROWS(KGB_NT, 8);
+    else KGB_ROWS(KGB_NN, 8);
+#undef KGB_ROWS
     KGB_LAUNCH_OK();
     return KGB_OK;
   }

@@ -19,7 +19,10 @@ M = 20371
 shapes = [("NT Z G->S", _lib.KGB_NT, M, 768, 128), ("NT Z G->G", _lib.KGB_NT, M, 640, 128), ("NT root", _lib.KGB_NT, M, 128, 128),
           ("NN dA", _lib.KGB_NN, M, 768, 128), ("NT af", _lib.KGB_NT, M, 128, 768), ("NN dx xf", _lib.KGB_NN, M, 128, 768),
           ("TN dW xf", _lib.KGB_TN, 768, 128, M), ("TN dW af", _lib.KGB_TN, 128, 768, M), ("NT GO", _lib.KGB_NT, 4563, 256, 128),
-          ("NT SNP/8 root", _lib.KGB_NT, 98032, 128, 128)]
+          ("NT SNP/8 root", _lib.KGB_NT, 98032, 128, 128), ("NT SNP root", _lib.KGB_NT, 784256, 128, 128),
+          ("NN SNP dx", _lib.KGB_NN, 784256, 128, 128), ("TN SNP dWr", _lib.KGB_TN, 128, 128, 784256)]
+if "--big" in sys.argv:
+    shapes = shapes[-4:]
 for name, lay, m, n, k in shapes:
     if lay == _lib.KGB_NT:
         a, b = torch.randn(m, k, device=dev), torch.randn(n, k, device=dev)
