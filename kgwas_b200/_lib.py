@@ -260,7 +260,10 @@ class Csr:
         the tickets zero)."""
         if self.n_hsegs == 0:
             return None, 0
-        key = (h, (self.hub.nv, self.hub.n_cta) if self.hub is not None else None)
+        # one scratch per launching stream: the ticket counters and partial rows of two gather-reduces over the same CSR
+        # that run on different streams (a captured step replaying next to an eager evaluation, model / best_model
+        # sharing a plan) must not meet
+        key = (h, (self.hub.nv, self.hub.n_cta) if self.hub is not None else None, _stream())
         if key not in self._scratch:
             nbytes = get_lib().kgb_spmm_scratch_bytes_csr(C.byref(self.struct), h)
             self._scratch[key] = torch.zeros(nbytes, dtype=torch.uint8, device=self.rowptr.device)
@@ -619,10 +622,11 @@ ATT_SOFTMAX, ATT_SIGMOID, ATT_RAW = 0, 1, 2
 def _gat_scratch(groups: Csr):
     if groups.n_hsegs == 0:
         return None, 0
-    if "gat" not in groups._scratch:
+    key = ("gat", _stream())
+    if key not in groups._scratch:
         nbytes = get_lib().kgb_gat_scratch_bytes(groups.n_hrows, groups.n_hsegs)
-        groups._scratch["gat"] = torch.zeros(nbytes, dtype=torch.uint8, device=groups.rowptr.device)
-    s = groups._scratch["gat"]
+        groups._scratch[key] = torch.zeros(nbytes, dtype=torch.uint8, device=groups.rowptr.device)
+    s = groups._scratch[key]
     return s, s.numel()
 
 
