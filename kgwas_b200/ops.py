@@ -45,21 +45,42 @@ def issue_order(ops, chain_priority=None):
     import heapq
     n = len(ops)
     preds = [set() for _ in range(n)]
-    last_w, readers = {}, {}
+
+    def overlap(a, b):
+        """keys are opaque hashables, or (storage, first byte, end byte) intervals of one allocation"""
+        if isinstance(a, tuple) and isinstance(b, tuple) and len(a) == 3 and len(b) == 3:
+            return a[0] == b[0] and a[1] < b[2] and b[1] < a[2]
+        return a == b
+
+    def inside(a, b):      # a fully covered by b
+        if isinstance(a, tuple) and isinstance(b, tuple) and len(a) == 3 and len(b) == 3:
+            return a[0] == b[0] and b[1] <= a[1] and a[2] <= b[2]
+        return a == b
+
+    live = []              # [key, last writer, readers since]: regions written so far (a superseded region is dropped)
     for i, (_, rk, wk) in enumerate(ops):
         for k in rk:
-            if k in last_w:
-                preds[i].add(last_w[k])
+            for e in live:
+                if overlap(k, e[0]):
+                    preds[i].add(e[1])
         for k in wk:
-            if k in last_w:
-                preds[i].add(last_w[k])
-            preds[i].update(readers.get(k, ()))
+            for e in live:
+                if overlap(k, e[0]):
+                    preds[i].add(e[1])
+                    preds[i].update(e[2])
         for k in wk:
-            last_w[k] = i
-            readers[k] = []
+            live = [e for e in live if not inside(e[0], k)]
+            live.append([k, i, []])
         for k in rk:
-            readers.setdefault(k, []).append(i)
+            hit = False
+            for e in live:
+                if overlap(k, e[0]) and e[1] != i:
+                    e[2].append(i)
+                    hit = True
+            if not hit and not any(overlap(k, e[0]) for e in live):
+                live.append([k, -1, [i]])          # read of something nobody wrote here: remember the reader (WAR)
         preds[i].discard(i)
+        preds[i].discard(-1)
     succs = [[] for _ in range(n)]
     for i in range(n):
         for p in preds[i]:
@@ -95,6 +116,20 @@ def issue_order(ops, chain_priority=None):
             if indeg[j] == 0:
                 heapq.heappush(heap, (cls[j], -tail[j], -desc[j], j))
     return preds, succs, order
+
+
+def _region(t):
+    """(storage, first byte, end byte) touched by a tensor view: launches on disjoint row-slices of one buffer (the flat
+    buffer that carries every shared node type through ONE all-reduce) do not depend on each other."""
+    es = t.element_size()
+    lo = t.storage_offset() * es
+    extent = 1
+    for size, stride in zip(t.shape, t.stride()):
+        if size == 0:
+            extent = 0
+            break
+        extent += (size - 1) * abs(stride)
+    return (t.untyped_storage().data_ptr(), lo, lo + max(extent, 1) * es)
 
 
 class _Sched:
@@ -137,8 +172,8 @@ class _Sched:
         """Record a launch.  ``fn`` takes no arguments, launches kernels only (no allocation) and must not depend on
         variables that change after this call (bind them with functools.partial / default arguments)."""
         self.keep.append((reads, writes, fn))
-        rk = [t.untyped_storage().data_ptr() for t in reads if t is not None]
-        wk = [t.untyped_storage().data_ptr() for t in writes if t is not None]
+        rk = [_region(t) for t in reads if t is not None]
+        wk = [_region(t) for t in writes if t is not None]
         self.ops.append((bool(big), fn, rk, wk, label, chain))
 
     def main_made(self, *ts):
@@ -261,6 +296,14 @@ class HeteroSageLayerFn(torch.autograd.Function):
         saved_A = {}
         # ---- phase 1 (main stream): allocate every buffer, do the [h,h]-sized parameter reshuffles -------------
         prep = {}
+        shared = [T for T in plan.dst_types if meta.exchange and T in meta.root_range]
+        flat_out, flat_off = None, {}
+        if shared:        # one buffer for the partial rows of every shared type: ONE all-reduce per pass
+            off = 0
+            for T in shared:
+                flat_off[T] = off
+                off += plan.num_nodes[T]
+            flat_out = _empty(off, h, Wl)
         for T in plan.dst_types:
             a, b = plan.rel_range[T]
             scale = meta.rel_scale[T]
@@ -279,7 +322,8 @@ class HeteroSageLayerFn(torch.autograd.Function):
                     job_bufs.append((Wl[lo:hi].reshape(job.R * h, h), _empty(job.n_src, job.R * h, Wl)))
                 else:                      # A = gather-reduce, then out += A . [W_1|..|W_R]^T
                     job_bufs.append((Wl[lo:hi].permute(1, 0, 2).reshape(h, job.R * h), _empty(n_t, job.R * h, Wl)))
-            prep[T] = (_empty(n_t, h, Wl), Wr[a:b].sum(0), bias, job_bufs)
+            out_T = flat_out[flat_off[T]:flat_off[T] + n_t] if T in flat_off else _empty(n_t, h, Wl)
+            prep[T] = (out_T, Wr[a:b].sum(0), bias, job_bufs)
             if T == head_T:
                 pred = _empty(n_t, 1, Wl)
         # ---- phase 2: record every launch with the scheduler (nothing runs yet), then let it issue them: big kernels
@@ -346,13 +390,14 @@ class HeteroSageLayerFn(torch.autograd.Function):
                     saved_A[(T, ji)] = buf
             if T == head_T and not head_in_spmm:
                 sch.run(big_T, P(_lib.rowdot, out, w_head, pred, h, 1, 0), (out, w_head), (pred,), "fwd head", T)
-            if meta.exchange and T in meta.root_range:
-                def exchange(out=out, relu=meta.relu):
-                    import torch.distributed as dist
-                    dist.all_reduce(out, op=dist.ReduceOp.SUM)      # partial rows of every rank -> the full rows
-                    if relu:
-                        out.relu_()
-                sch.run(False, exchange, (out,), (out,), f"fwd all-reduce {T}", ("comm", T))
+
+        if flat_out is not None:
+            def exchange(buf=flat_out, relu=meta.relu):
+                import torch.distributed as dist
+                dist.all_reduce(buf, op=dist.ReduceOp.SUM)          # partial rows of every rank -> the full rows
+                if relu:
+                    buf.relu_()
+            sch.run(False, exchange, (flat_out,), (flat_out,), "fwd all-reduce shared types", ("comm",))
         outs = [prep[T][0] for T in plan.dst_types]
         sch.keep.append(prep)
         sch.join()
@@ -406,6 +451,33 @@ class HeteroSageLayerFn(torch.autograd.Function):
         P = functools.partial
         order = sorted(range(len(plan.dst_types)), key=lambda i: -plan.num_nodes[plan.dst_types[i]])
         late = []       # recorded after everything else: small consumers of a big gather-reduce (see below)
+        # Sharded runs: d_out of a shared type is this rank's gradient w.r.t. the (ReLU-ed) SUM over ranks.  Mask every such
+        # gradient into one flat buffer, sum it over ranks with ONE all-reduce -- every rank's partial rows entered the
+        # forward sum with weight one -- and only then use the slices.
+        g_shared = {}
+        if meta.exchange:
+            sh = [(plan.dst_types[i], d_outs[i]) for i in order
+                  if plan.dst_types[i] in meta.root_range and d_outs[i] is not None]
+            if sh:
+                gflat = _empty(sum(plan.num_nodes[T] for T, _ in sh), h, Wl)
+                off = 0
+                for T, d_out in sh:
+                    n_t = plan.num_nodes[T]
+                    gT = g_shared[T] = gflat[off:off + n_t]
+                    off += n_t
+                    dy = d_out.contiguous()
+
+                    def mask(g=gT, dy=dy, y=outs[T], relu=meta.relu, scale=meta.rel_scale[T]):
+                        if relu:
+                            _lib.relu_bwd_fused(g, h, dy=dy, y=y, scale=scale)
+                        else:
+                            torch.mul(dy, scale, out=g)
+                    sch.run(False, mask, (dy, outs[T]), (gT,), f"bwd mask {T}", T)
+
+                def exchange_bwd(buf=gflat):
+                    import torch.distributed as dist
+                    dist.all_reduce(buf, op=dist.ReduceOp.SUM)
+                sch.run(False, exchange_bwd, (gflat,), (gflat,), "bwd all-reduce shared types", ("comm",))
         for T, d_out in [(plan.dst_types[i], d_outs[i]) for i in order]:
             dp = d_pred if T == head_T else None
             if d_out is None and dp is None:
@@ -427,20 +499,8 @@ class HeteroSageLayerFn(torch.autograd.Function):
                         (dy, outs[T], dpc, w_head), (g, sums), f"bwd relu {T}", T)
                 if dp is not None:
                     d_w_head = sums[1:2]
-            elif meta.exchange and T in meta.root_range:
-                # d_out is this rank's gradient w.r.t. the (ReLU-ed) SUM over ranks: mask it, sum it over ranks -- every
-                # rank's partial rows entered that sum with weight one -- and only then use it
-                g = _empty(n_t, h, Wl)
-                dy = d_out.contiguous()
-
-                def exchange_bwd(g=g, dy=dy, y=outs[T], relu=meta.relu, scale=scale):
-                    import torch.distributed as dist
-                    if relu:
-                        _lib.relu_bwd_fused(g, h, dy=dy, y=y, scale=scale)
-                    else:
-                        torch.mul(dy, scale, out=g)
-                    dist.all_reduce(g, op=dist.ReduceOp.SUM)
-                sch.run(False, exchange_bwd, (dy, outs[T]), (g,), f"bwd all-reduce {T}", ("comm", T))
+            elif T in g_shared:
+                g = g_shared[T]                                   # masked and summed over ranks above
             else:
                 g = d_out.contiguous()
                 if scale != 1.0:

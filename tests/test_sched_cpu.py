@@ -73,3 +73,21 @@ def test_longest_chain_first_among_ready_big_launches(monkeypatch):
     _, _, order = issue_order(ops)
     assert order.index(4) < order.index(2)
     assert order.index(0) < order.index(2) and order.index(1) < order.index(2) and order.index(4) < order.index(5)
+
+
+def test_row_slices_of_one_buffer_are_independent_regions():
+    """(storage, first byte, end byte) keys: launches on disjoint row-slices of one flat buffer do not depend on each
+    other; a launch on the whole buffer (the all-reduce of every shared node type) depends on all of them, and whatever
+    reads a slice afterwards depends on that launch."""
+    buf, lo, mid, hi = 7, 0, 4096, 8192
+    ops = [(False, ["x"], [(buf, lo, mid)]),            # 0 writes slice A
+           (False, ["y"], [(buf, mid, hi)]),            # 1 writes slice B
+           (False, [(buf, lo, hi)], [(buf, lo, hi)]),   # 2 all-reduce in place over the whole buffer
+           (False, [(buf, lo, mid)], ["outA"]),         # 3 reads slice A
+           (False, ["z"], [(buf, mid, hi)])]            # 4 overwrites slice B (WAR on 2 and nothing else of A)
+    preds, _, order = issue_order(ops)
+    assert preds[0] == set() and preds[1] == set()
+    assert preds[2] == {0, 1}
+    assert preds[3] == {2}
+    assert 2 in preds[4] and 3 not in preds[4]
+    assert sorted(order) == [0, 1, 2, 3, 4]
