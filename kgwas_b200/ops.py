@@ -67,7 +67,7 @@ def issue_order(ops, chain_priority=None):
             for e in live:
                 if overlap(k, e[0]):
                     preds[i].add(e[1])
-                    preds[i].update(e[2])
+                    preds[i].update(r for r, rkey in e[2] if overlap(k, rkey))
         for k in wk:
             live = [e for e in live if not inside(e[0], k)]
             live.append([k, i, []])
@@ -75,10 +75,10 @@ def issue_order(ops, chain_priority=None):
             hit = False
             for e in live:
                 if overlap(k, e[0]) and e[1] != i:
-                    e[2].append(i)
+                    e[2].append((i, k))
                     hit = True
             if not hit and not any(overlap(k, e[0]) for e in live):
-                live.append([k, -1, [i]])          # read of something nobody wrote here: remember the reader (WAR)
+                live.append([k, -1, [(i, k)]])     # read of something nobody wrote here: remember the reader (WAR)
         preds[i].discard(i)
         preds[i].discard(-1)
     succs = [[] for _ in range(n)]
