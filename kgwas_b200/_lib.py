@@ -548,6 +548,10 @@ def relu_bwd_fused(g: torch.Tensor, h: int, *, dy=None, y=None, dp=None, wv=None
         if t is not None:
             _f32c(t, "relu_bwd_fused " + name)
     m = g.size(0)
+    if m == 0:                       # a node type without rows in this mini-batch: nothing to mask, zero column sums
+        if sums is not None:
+            sums.zero_()
+        return g
     lib = get_lib()
     ws = None
     if sums is not None:

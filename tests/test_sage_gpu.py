@@ -196,3 +196,37 @@ def test_graphed_step_matches_eager(cuda):
     assert torch.allclose(l0, l1, rtol=1e-6)
     for k in s0:
         assert torch.allclose(s0[k], s1[k], rtol=1e-5, atol=1e-7), k
+
+
+@pytest.mark.parametrize("backbone", ["SAGE", "GAT"])
+def test_a_node_type_without_rows_in_the_batch(cuda, backbone):
+    """A mini-batch may lack a node type entirely (edge-sampled or tiny KGs): zero-row operands must flow through
+    forward AND backward (empty contractions write zeros) and still match the oracle."""
+    import kgwas_b200
+    from oracle import kgwas_oracle as O
+    h = 64
+    g = torch.Generator().manual_seed(0)
+    n = {"SNP": 40, "Gene": 9, "CellularComponent": 0}
+    ei = {("SNP", "a", "Gene"): torch.stack([torch.randint(0, 40, (120,), generator=g), torch.randint(0, 9, (120,), generator=g)]),
+          ("Gene", "rev_a", "SNP"): torch.stack([torch.randint(0, 9, (120,), generator=g), torch.randint(0, 40, (120,), generator=g)]),
+          ("Gene", "g", "Gene"): torch.stack([torch.randint(0, 9, (30,), generator=g), torch.randint(0, 9, (30,), generator=g)]),
+          ("Gene", "c", "CellularComponent"): torch.zeros((2, 0), dtype=torch.int64),
+          ("CellularComponent", "rev_c", "Gene"): torch.zeros((2, 0), dtype=torch.int64)}
+    x = {t: torch.randn(c, h, generator=g) for t, c in n.items()}
+    mk = (lambda m: m.SAGEConv((-1, -1), h)) if backbone == "SAGE" else (lambda m: m.GATConv((-1, -1), h, heads=1, add_self_loops=False))
+    torch.manual_seed(1)
+    ref = O.HeteroConv({et: mk(O) for et in ei}, aggr="sum")
+    xr = {k: v.clone().requires_grad_() for k, v in x.items()}
+    out_r = ref(xr, ei)
+    sum(v.relu().sum() for v in out_r.values()).backward()
+    ours = kgwas_b200.HeteroConv({et: mk(kgwas_b200) for et in ei}, aggr="sum")
+    missing, unexpected = ours.load_state_dict(ref.state_dict(), strict=False)
+    assert not unexpected
+    ours = ours.to(cuda)
+    xc = {k: v.to(cuda).requires_grad_() for k, v in x.items()}
+    out = ours(xc, {k: v.to(cuda) for k, v in ei.items()})
+    sum(v.relu().sum() for v in out.values()).backward()
+    assert set(out.keys()) == set(out_r.keys()) and out["CellularComponent"].shape == (0, h)
+    for t in ("SNP", "Gene"):
+        assert torch.allclose(out[t].detach().cpu(), out_r[t].detach(), rtol=1e-4, atol=1e-5), t
+        assert torch.allclose(xc[t].grad.cpu(), xr[t].grad, rtol=1e-3, atol=1e-5), t
