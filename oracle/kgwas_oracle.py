@@ -10,7 +10,8 @@ PARITY STATUS: **partially pinned**.
   * The in-tree half of the reference (``kgwas/model.py``, ``kgwas/conv.py``) is executed
     *verbatim* from /root/reference by ``oracle/gen_golden_from_reference.py`` on top of a
     minimal stand-in for the PyG base classes (``oracle/pyg_standin``) and this oracle must
-    reproduce those outputs (``tests/golden/ref_*.pt``; see tests/test_oracle_golden.py).
+    reproduce those outputs (``tests/golden/ref_*.pt``: h = 32 models, and h = 128 / 256, L = 2 / 3
+    models on a 3 000-SNP KG with hub genes -- ``ref_mid_*.pt``; see tests/test_oracle_golden.py).
   * The third-party half (torch_geometric's ``SAGEConv`` / ``HeteroConv`` / ``MessagePassing``
     / ``softmax`` / ``scatter``) is NOT in /root/reference, is un-pinned there
     (requirements.txt:6, environment.yml:8-10) and cannot be installed here, so those
