@@ -294,7 +294,10 @@ class HeteroSageLayerFn(torch.autograd.Function):
         ctx.set_materialize_grads(False)
         x = dict(zip(meta.node_types, [t.contiguous() for t in xs]))
         saved_A = {}
-        # ---- phase 1 (main stream): allocate every buffer, do the [h,h]-sized parameter reshuffles -------------
+        # ---- phase 1: allocate every buffer; the [h,h]-sized parameter reshuffles (summed root weights and biases,
+        # transposed job weights) are RECORDED like any other launch -- ~20 tiny kernels that used to run on the caller's
+        # stream ahead of the first SNP-sized kernel of every pass (~100 us per pass) now sit on the side streams
+        sch = _Sched(Wl.device, chain_priority=True if meta.exchange else None)
         prep = {}
         shared = [T for T in plan.dst_types if meta.exchange and T in meta.root_range]
         flat_out, flat_off = None, {}
@@ -308,9 +311,15 @@ class HeteroSageLayerFn(torch.autograd.Function):
             a, b = plan.rel_range[T]
             scale = meta.rel_scale[T]
             n_t = plan.num_nodes[T]
-            bias = bl[a:b].sum(0)
-            if scale != 1.0:
-                bias = bias * scale
+            bias = torch.empty(h, dtype=torch.float32, device=Wl.device)
+            w_root = _empty(h, h, Wl)
+
+            def root_operands(bias=bias, w_root=w_root, bl_s=bl[a:b], wr_s=Wr[a:b], scale=scale):
+                torch.sum(bl_s, dim=0, out=bias)
+                if scale != 1.0:
+                    bias.mul_(scale)
+                torch.sum(wr_s, dim=0, out=w_root)
+            sch.run(False, root_operands, (bl[a:b], Wr[a:b]), (bias, w_root), f"prep root {T}", T)
             job_bufs = []
             for job in plan.jobs[T]:
                 job.schedule(h)
@@ -321,16 +330,20 @@ class HeteroSageLayerFn(torch.autograd.Function):
                 if job.mode == "xf":       # Z = X_src . [W_1;..;W_R]^T  (view: rows k*h.. = W_l^k)
                     job_bufs.append((Wl[lo:hi].reshape(job.R * h, h), _empty(job.n_src, job.R * h, Wl)))
                 else:                      # A = gather-reduce, then out += A . [W_1|..|W_R]^T
-                    job_bufs.append((Wl[lo:hi].permute(1, 0, 2).reshape(h, job.R * h), _empty(n_t, job.R * h, Wl)))
+                    w_t = _empty(h, job.R * h, Wl)
+
+                    def transpose_w(w_t=w_t, src=Wl[lo:hi], R=job.R):
+                        w_t.view(h, R, h).copy_(src.permute(1, 0, 2))
+                    sch.run(False, transpose_w, (Wl[lo:hi],), (w_t,), f"prep W af {job.src_type}->{T}", T)
+                    job_bufs.append((w_t, _empty(n_t, job.R * h, Wl)))
             out_T = flat_out[flat_off[T]:flat_off[T] + n_t] if T in flat_off else _empty(n_t, h, Wl)
-            prep[T] = (out_T, Wr[a:b].sum(0), bias, job_bufs)
+            prep[T] = (out_T, w_root, bias, job_bufs)
             if T == head_T:
                 pred = _empty(n_t, 1, Wl)
         # ---- phase 2: record every launch with the scheduler (nothing runs yet), then let it issue them: big kernels
         # back to back on this stream, small chains on high-priority side streams, ordered by the data they touch ----
-        # sharded runs: the gather with a cross-rank sum behind it goes first (measured at N = 2: 4.27 -> 4.16 ms/step; on one
-        # GPU the same order only moves the contention, 6.22 -> 6.37 ms)
-        sch = _Sched(Wl.device, chain_priority=True if meta.exchange else None)
+        # (sharded runs: the gather with a cross-rank sum behind it goes first -- measured at N = 2: 4.27 -> 4.16 ms/step; on one
+        #  GPU the same order only moves the contention, 6.22 -> 6.37 ms)
         P = functools.partial
         for T in sorted(plan.dst_types, key=lambda t: -plan.num_nodes[t]):
             scale = meta.rel_scale[T]
