@@ -632,7 +632,8 @@ def spmm_roofline(args, r, ms_step):
         except Exception:                                     # noqa: BLE001
             pass
     return {"bound": "hbm",
-            "kernel": f"kgb_spmm = lean::k_spmm_lean<{r.h // 128}> + hub::k_hub_tile (segmented gather-reduce, all kgb_spmm launches of a step)",
+            "kernel": f"kgb_spmm = lean::k_spmm_lean<{r.h // 128}> (segmented gather-reduce, all kgb_spmm launches of a step; "
+                      f"the opt-in hub-tile path hub::k_hub_tile is {'ON' if os.environ.get('KGB_SPMM_HUB') == '1' else 'off'})",
             "achieved": spmm_gbs, "peak": peak, "unit": "GB/s", "frac": spmm_gbs / peak,
             "traffic": traffic, "traffic_source": traffic_src,
             "peak_source": peak_src, "launches_per_step": n_spmm // prof_steps,
