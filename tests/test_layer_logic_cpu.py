@@ -163,3 +163,40 @@ def test_model_with_fused_head_matches_oracle(monkeypatch, bs):
         assert (p_r[k].grad is None) == (p_o[k].grad is None), k
         if p_r[k].grad is not None:
             assert (p_r[k].grad - p_o[k].grad).abs().max().item() <= 2e-4 * scale, k
+
+
+def test_multi_source_job_is_the_union_of_its_parts(monkeypatch):
+    """plan.MultiXfJob (one gather-reduce over one Z table for all small transform-first jobs into a destination type):
+    integer bookkeeping -- every destination row gathers exactly the union of what the separate jobs gather, from the
+    re-based table rows, with the same mean weights; the transposed CSR is its exact transpose."""
+    import numpy as np
+    _cpu_kernels.install(monkeypatch)
+    from kgwas_b200 import make_synth_kg
+    from kgwas_b200 import plan as P
+    P.clear_plan_cache()
+    data = make_synth_kg(0.01, 3, hidden=32)
+    num_nodes = {t: int(x.size(0)) for t, x in data.x_dict.items()}
+    sep = P.get_plan(data.edge_index_dict, num_nodes, merge_xf=False)
+    mer = P.get_plan(data.edge_index_dict, num_nodes, merge_xf=True)
+    assert sep is not mer and mer.n_edges == sep.n_edges
+    merged = [j for j in mer.jobs["Gene"] if getattr(j, "multi", False)]
+    assert len(merged) == 1 and len(merged[0].parts) >= 2
+    job = merged[0]
+    parts = {j.src_type: j for j in sep.jobs["Gene"] if j.mode == "xf" and j.src_type in [p[0] for p in job.parts]}
+    assert job.n_edges == sum(p.n_edges for p in parts.values())
+    rp, col, w = job.csr.rowptr.numpy(), job.csr.col.numpy(), job.w_mean.numpy()
+    for t in range(num_nodes["Gene"]):
+        got = sorted(zip(col[rp[t]:rp[t + 1]].tolist(), np.round(w[rp[t]:rp[t + 1]], 7).tolist()))
+        want = []
+        for (S, R, lo, hi, n_src, off) in job.parts:
+            pj = parts[S]
+            assert (pj.R, pj.n_src, pj.rel_ids[0], pj.rel_ids[-1] + 1) == (R, n_src, lo, hi)
+            prp, pcol, pw = pj.csr.rowptr.numpy(), pj.csr.col.numpy(), pj.w_mean.numpy()
+            want += list(zip((pcol[prp[t]:prp[t + 1]] + off).tolist(), np.round(pw[prp[t]:prp[t + 1]], 7).tolist()))
+        assert got == sorted(want), t
+    # transposed CSR: same (row, column, weight) triples
+    trp, tcol, tw = job.tcsr.rowptr.numpy(), job.tcsr.col.numpy(), job.w_mean_t.numpy()
+    fwd = sorted((int(c), t, round(float(x), 7)) for t in range(num_nodes["Gene"]) for c, x in zip(col[rp[t]:rp[t + 1]], w[rp[t]:rp[t + 1]]))
+    bwd = sorted((r, int(c), round(float(x), 7)) for r in range(job.total_rows) for c, x in zip(tcol[trp[r]:trp[r + 1]], tw[trp[r]:trp[r + 1]]))
+    assert fwd == bwd
+    P.clear_plan_cache()
