@@ -117,14 +117,19 @@ class GpuFullNeighborSampler:
         dev = next(iter(self.edges.values())).device
         self.device = dev
         self.adj = {}
-        for et in self.edge_types:
-            ei = self.edges[et]
-            csr, eperm, _, _ = _lib.csr_build(ei[0], ei[1], self.num_nodes[et[0]], self.num_nodes[et[2]], transposed=False)
-            self.adj[et] = (csr.rowptr, csr.col, eperm)                 # in-edges of a node in original edge order
+        with torch.cuda.device(dev):                    # the C ABI launches on the current device: follow the data
+            for et in self.edge_types:
+                ei = self.edges[et]
+                csr, eperm, _, _ = _lib.csr_build(ei[0], ei[1], self.num_nodes[et[0]], self.num_nodes[et[2]], transposed=False)
+                self.adj[et] = (csr.rowptr, csr.col, eperm)             # in-edges of a node in original edge order
         self.local = {t: torch.full((n,), -1, dtype=torch.int32, device=dev) for t, n in self.num_nodes.items()}
         self.firstpos = {t: torch.full((n,), 2 ** 31 - 1, dtype=torch.int32, device=dev) for t, n in self.num_nodes.items()}
 
     def sample(self, seed_type: str, seeds):
+        with torch.cuda.device(self.device):
+            return self._sample(seed_type, seeds)
+
+    def _sample(self, seed_type: str, seeds):
         lib, dev = self._lib, self.device
         seeds = torch.as_tensor(seeds, device=dev).to(torch.int32).contiguous()
         count = {t: 0 for t in self.num_nodes}

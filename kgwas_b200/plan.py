@@ -272,7 +272,14 @@ def get_plan(edge_index_dict, num_nodes: Dict[str, int], conv_keys=None, merge_x
     for et, ei in edge_index_dict.items():
         if ei.dtype != torch.int64 or ei.dim() != 2 or ei.size(0) != 2:
             raise ValueError(f"edge_index of {et} must be int64 [2, E], got {ei.dtype} {tuple(ei.shape)}")
-    p = LayerPlan(edge_index_dict, num_nodes, conv_keys, merge_xf)
+    # the plan's kernels (CSR build, heavy-row tables) launch on the CURRENT device: build under the graph's device so that
+    # `KGWAS(data, device='cuda:1')` works without `torch.cuda.set_device` (kgwas/kgwas.py:38-39)
+    dev = next((ei.device for ei in edge_index_dict.values() if ei.is_cuda), None)
+    if dev is not None and dev.index != torch.cuda.current_device():
+        with torch.cuda.device(dev):
+            p = LayerPlan(edge_index_dict, num_nodes, conv_keys, merge_xf)
+    else:
+        p = LayerPlan(edge_index_dict, num_nodes, conv_keys, merge_xf)
     plan_builds += 1
     _CACHE.insert(0, p)
     del _CACHE[_CACHE_SIZE:]

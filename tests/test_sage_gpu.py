@@ -230,3 +230,38 @@ def test_a_node_type_without_rows_in_the_batch(cuda, backbone):
     for t in ("SNP", "Gene"):
         assert torch.allclose(out[t].detach().cpu(), out_r[t].detach(), rtol=1e-4, atol=1e-5), t
         assert torch.allclose(xc[t].grad.cpu(), xr[t].grad, rtol=1e-3, atol=1e-5), t
+
+
+@pytest.mark.parametrize("backbone", ["SAGE", "GAT"])
+def test_model_on_a_non_current_device(cuda, backbone):
+    """``KGWAS(data, device='cuda:1')`` without ``torch.cuda.set_device`` (kgwas/kgwas.py:38-39): the autograd Functions
+    enter the device of their inputs, so launches, streams and allocations follow the data; a direct C-ABI call with a
+    tensor of another device raises instead of launching on the wrong GPU.  Needs two visible GPUs."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import kgwas_b200
+    from kgwas_b200 import _lib, make_synth_kg
+    h = 128
+    data = make_synth_kg(scale=0.003, seed=4, hidden=h)
+    torch.manual_seed(0)
+    m0 = kgwas_b200.HeteroGNN(data, h, 1, 2, backbone, "sum", h, h, h, 1, no_relu=True)
+    d0 = data.to("cuda:0")
+    m0 = m0.to("cuda:0")
+    out0 = m0.forward_from_hidden({k: v.clone().requires_grad_() for k, v in d0.x_dict.items()}, d0.edge_index_dict, 50)
+    out0.sum().backward()
+    kgwas_b200.plan.clear_plan_cache()
+    assert torch.cuda.current_device() == 0
+    m1 = kgwas_b200.HeteroGNN(data, h, 1, 2, backbone, "sum", h, h, h, 1, no_relu=True)
+    m1.load_state_dict(m0.state_dict())
+    m1 = m1.to("cuda:1")
+    d1 = data.to("cuda:1")
+    out1 = m1.forward_from_hidden({k: v.clone().requires_grad_() for k, v in d1.x_dict.items()}, d1.edge_index_dict, 50)
+    out1.sum().backward()
+    torch.cuda.synchronize("cuda:1")
+    assert torch.cuda.current_device() == 0
+    assert torch.allclose(out1.cpu(), out0.cpu(), rtol=1e-5, atol=1e-6)
+    assert torch.allclose(m1.lin.weight.grad.cpu(), m0.lin.weight.grad.cpu(), rtol=1e-4, atol=1e-6)
+    x1 = torch.randn(64, h, device="cuda:1")
+    with pytest.raises(_lib.KgbError):
+        _lib.rowdot(x1, torch.randn(1, h, device="cuda:1"), torch.empty(64, 1, device="cuda:1"), h, 1, 0)
+    kgwas_b200.plan.clear_plan_cache()
